@@ -1,0 +1,109 @@
+"""The CPU oracle (oracle/cir_oracle.py) against the fixtures the UNMODIFIED reference
+produced (tests/golden/make_golden.py).  This is the pin for every parity claim."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cir_b200 as cir
+from oracle import cir_oracle as O
+
+syn = cir.synthetic
+torch.set_num_threads(os.cpu_count() or 1)
+
+
+def _load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="module")
+def small(golden_dir):
+    g = _load(golden_dir, "pipeline_small.npz")
+    sd1 = syn.make_stage1_state_dict(int(g["seed"]), 384, str(g["style"]))
+    sd2 = syn.make_stage2_state_dict(int(g["seed"]), 384, str(g["style"]), head_gain=float(g["head_gain"]))
+    images = syn.make_images(int(g["G"]), 384, seed=1)
+    with torch.no_grad():
+        tokens2 = O.vit_forward(sd2, images)
+    return g, sd1, sd2, images, tokens2
+
+
+def test_synthetic_inputs_reproduce(small):
+    g = small[0]
+    ref_idx, target_idx, ids, mask = syn.make_queries(int(g["Q"]), int(g["G"]), int(g["L"]), seed=3,
+                                                       min_len=int(g["min_len"]))
+    assert np.array_equal(ref_idx.numpy(), g["ref_idx"])
+    assert np.array_equal(target_idx.numpy(), g["target_idx"])
+    assert np.array_equal(ids.numpy(), g["ids"])
+    assert np.array_equal(mask.numpy(), g["mask"])
+    assert (g["mask"].sum(1) < g["mask"].shape[1]).any(), "fixture must contain ragged (padded) captions"
+
+
+def test_vit_matches_reference(small):
+    g, _, _, _, tokens2 = small
+    assert np.abs(tokens2[:, ::48, ::16].numpy() - g["tokens2_sample"]).max() < 2e-5
+    assert np.abs(tokens2[:, 0, :].numpy() - g["tokens2_cls"]).max() < 2e-5
+    assert np.abs(tokens2.mean((1, 2)).numpy() - g["tokens2_mean"]).max() < 1e-6
+
+
+def test_stage1_matches_reference(small):
+    g, sd1, _, images, tokens2 = small
+    ids, mask = torch.tensor(g["ids"]), torch.tensor(g["mask"])
+    ref_idx = torch.tensor(g["ref_idx"])
+    with torch.no_grad():
+        tokens1 = O.vit_forward(sd1, images)
+        assert np.abs(tokens1[:, 0, :].numpy() - g["tokens1_cls"]).max() < 2e-5
+        g_emb = O.stage1_gallery_embedding(sd1, tokens1)
+        assert np.abs(g_emb.numpy() - g["g_emb"]).max() < 1e-5
+        q_emb = O.stage1_query_embedding(sd1, O.stage1_hidden(sd1, tokens1[ref_idx], ids, mask))
+        q_emb = torch.nn.functional.normalize(q_emb)          # CIRR: src/validate.py:311
+        assert np.abs(q_emb.numpy() - g["q_emb"]).max() < 1e-5
+        # z_t uses the stage-II ViT's tokens: src/validate_stage2.py:243-244,293
+        z = O.stage1_hidden(sd1, tokens2[ref_idx], ids, mask)
+        assert np.abs(z.numpy() - g["z_t"]).max() < 5e-5
+    # top-K from the reference's own fp32 embeddings must be bit-exact
+    dist, idx = O.stage1_topk(torch.tensor(g["q_emb"]), torch.tensor(g["g_emb"]), ref_idx, int(g["K"]))
+    assert np.array_equal(idx.numpy().astype(np.int32), g["cand_idx"])
+    assert np.array_equal(dist.numpy(), g["distances_topk"])
+
+
+def test_stage2_matches_reference(small):
+    g, _, sd2, _, tokens2 = small
+    ids, mask = torch.tensor(g["ids"]), torch.tensor(g["mask"])
+    z_t = torch.tensor(g["z_t"])
+    cand_idx = torch.tensor(g["cand_idx"]).long()
+    with torch.no_grad():
+        for q in range(int(g["Q"])):
+            f = O.stage2_features(sd2, z_t[q:q + 1], ids[q:q + 1], mask[q:q + 1], tokens2[cand_idx[q]])
+            assert np.abs(f.numpy() - g["feats"][q]).max() < 1e-4
+            s = O.stage2_head(sd2, f)
+            assert np.abs(s.numpy() - g["scores"][q]).max() < 1e-4
+
+
+def test_rerank_and_recall_bit_exact_from_reference_scores(small):
+    g = small[0]
+    scores = torch.tensor(g["scores"])
+    assert np.array_equal(O.rerank_order(scores).numpy().astype(np.int32), g["order"])
+    lab = O.sorted_labels(scores, g["k_labels"])
+    assert np.array_equal(lab.numpy(), g["sorted_labels"])
+    assert O.recall_at(lab, (1, 2, 3, 4)) == list(g["recalls"])
+
+
+def test_stage2_L32_reference_init(golden_dir):
+    g = _load(golden_dir, "stage2_L32.npz")
+    sd2 = syn.make_stage2_state_dict(int(g["seed"]), 384, str(g["style"]), head_gain=float(g["head_gain"]))
+    images = syn.make_images(int(g["G"]), 384, seed=1)
+    with torch.no_grad():
+        tokens2 = O.vit_forward(sd2, images)
+        s = O.stage2_score(sd2, torch.tensor(g["z_t"])[0:1], torch.tensor(g["ids"]), torch.tensor(g["mask"]),
+                           tokens2[torch.tensor(g["cand_idx"][0]).long()])
+    assert np.abs(s.numpy() - g["scores"][0]).max() < 1e-5
+
+
+def test_empty_positive_rows_are_filled(small):
+    g, sd1, sd2, _, tokens2 = small
+    k_labels = np.zeros_like(g["k_labels"])
+    out = O.stage2_predictions(sd1, sd2, tokens2, torch.tensor(g["ref_idx"]), torch.tensor(g["ids"]),
+                               torch.tensor(g["mask"]), torch.tensor(g["cand_idx"]), k_labels)
+    assert torch.all(out == O.NEG_FILL)
