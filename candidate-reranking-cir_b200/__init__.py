@@ -18,8 +18,8 @@ def __getattr__(name):
     # Heavy modules (they dlopen the CUDA library) load lazily so that ``synthetic`` stays
     # importable on machines without the built extension.
     import importlib
-    if name in ("native", "engine", "blip_stage1", "blip_stage2", "validate", "validate_stage2",
-                "distributed", "topk_file"):
+    if name in ("native", "engine", "schedule", "blip", "blip_stage1", "blip_stage2", "validate",
+                "validate_stage2", "distributed", "topk_file", "build"):
         return importlib.import_module(f"{__name__}.{name}")
     for mod in ("blip_stage1", "blip_stage2"):
         if name in ("BLIP_Retrieval", "BLIP_NLVR"):

@@ -1,0 +1,86 @@
+// Shared host/device helpers for libcir_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/cir_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+struct cir_ctx {
+  int device;
+  int dtype;            // CIR_DTYPE_*
+  int gemm_impl;        // CIR_GEMM_*
+  cudaStream_t stream;
+  int num_sms;
+  int64_t launches;
+  void* encode_tiled;   // cuTensorMapEncodeTiled entry point (PFN), resolved lazily
+};
+
+void cir_set_error(const char* fmt, ...);
+
+#define CIR_CHECK_ARG(cond, ...)                      \
+  do {                                                \
+    if (!(cond)) {                                    \
+      cir_set_error(__VA_ARGS__);                     \
+      return CIR_EINVAL;                              \
+    }                                                 \
+  } while (0)
+
+#define CIR_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      cir_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return CIR_ECUDA;                                                                  \
+    }                                                                                    \
+  } while (0)
+
+#define CIR_LAUNCH_CHECK(ctx)                                                            \
+  do {                                                                                   \
+    (ctx)->launches++;                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) {                                                            \
+      cir_set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return CIR_ECUDA;                                                                  \
+    }                                                                                    \
+  } while (0)
+
+#define CIR_TRY(call)            \
+  do {                           \
+    int r__ = (call);            \
+    if (r__ != CIR_OK) return r__; \
+  } while (0)
+
+static inline size_t act_size(const cir_ctx* ctx) { return ctx->dtype == CIR_DTYPE_F32 ? 4 : 2; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- device-side scalar conversion helpers, usable with T = float or bf16 ---------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// internal cross-file entry points
+int cir_gemm_simt(cir_ctx* ctx, const cir_gemm_args* a);
+int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a);

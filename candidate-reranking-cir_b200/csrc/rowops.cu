@@ -1,0 +1,287 @@
+// Bandwidth-bound row kernels: LayerNorm (+residual, twin gains), embeddings, gathers, casts,
+// L2-normalise, ViT patchify/assemble, score-head dot.  One warp per 768-wide row, 16-byte
+// vector accesses, fp32 statistics.
+#include "common.cuh"
+
+namespace {
+
+constexpr int D = CIR_HIDDEN;          // 768
+constexpr int PER_LANE = D / 32;       // 24 contiguous elements per lane
+constexpr int WARPS = 8;
+
+template <typename T> __device__ __forceinline__ void load24(const T* p, float (&v)[PER_LANE]);
+template <> __device__ __forceinline__ void load24<float>(const float* p, float (&v)[PER_LANE]) {
+#pragma unroll
+  for (int i = 0; i < PER_LANE; i += 4) {
+    float4 t = *reinterpret_cast<const float4*>(p + i);
+    v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+  }
+}
+template <> __device__ __forceinline__ void load24<bf16>(const bf16* p, float (&v)[PER_LANE]) {
+#pragma unroll
+  for (int i = 0; i < PER_LANE; i += 8) {
+    uint4 t = *reinterpret_cast<const uint4*>(p + i);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int q = 0; q < 4; q++) { float2 f = __bfloat1622float2(h[q]); v[i + 2 * q] = f.x; v[i + 2 * q + 1] = f.y; }
+  }
+}
+template <typename T> __device__ __forceinline__ void store24(T* p, const float (&v)[PER_LANE]);
+template <> __device__ __forceinline__ void store24<float>(float* p, const float (&v)[PER_LANE]) {
+#pragma unroll
+  for (int i = 0; i < PER_LANE; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+template <> __device__ __forceinline__ void store24<bf16>(bf16* p, const float (&v)[PER_LANE]) {
+#pragma unroll
+  for (int i = 0; i < PER_LANE; i += 8) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int q = 0; q < 4; q++) h[q] = __floats2bfloat162_rn(v[i + 2 * q], v[i + 2 * q + 1]);
+    *reinterpret_cast<uint4*>(p + i) = t;
+  }
+}
+
+__device__ __forceinline__ void layernorm24(float (&v)[PER_LANE], const float* gamma, const float* beta, float eps, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; i++) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; i++) { float d = v[i] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  float g[PER_LANE], b[PER_LANE];
+  load24<float>(gamma + lane * PER_LANE, g);
+  load24<float>(beta + lane * PER_LANE, b);
+#pragma unroll
+  for (int i = 0; i < PER_LANE; i++) v[i] = fmaf((v[i] - mean) * rstd, g[i], b[i]);
+}
+
+template <typename TX, typename TR, typename TY>
+__global__ void __launch_bounds__(WARPS * 32)
+add_layernorm_kernel(const TX* __restrict__ x, int64_t x_rows, const TR* __restrict__ res, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, int64_t rows_per_group, TY* __restrict__ y, int64_t rows, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float v[PER_LANE];
+  load24<TX>(x + (r % x_rows) * D + lane * PER_LANE, v);
+  if (res) {
+    float t[PER_LANE];
+    load24<TR>(res + r * D + lane * PER_LANE, t);
+#pragma unroll
+    for (int i = 0; i < PER_LANE; i++) v[i] += t[i];
+  }
+  const int64_t g = r / rows_per_group;
+  layernorm24(v, gamma + g * D, beta + g * D, eps, lane);
+  store24<TY>(y + r * D + lane * PER_LANE, v);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+bert_embeddings_kernel(const int32_t* __restrict__ ids, int64_t rows, int64_t L, const float* __restrict__ word,
+                       const float* __restrict__ pos, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int64_t l = r % L;
+  float v[PER_LANE], t[PER_LANE];
+  load24<float>(word + (int64_t)ids[r] * D + lane * PER_LANE, v);
+  load24<float>(pos + l * D + lane * PER_LANE, t);
+#pragma unroll
+  for (int i = 0; i < PER_LANE; i++) v[i] += t[i];
+  layernorm24(v, gamma, beta, 1e-12f, lane);
+  store24<T>(out + r * D + lane * PER_LANE, v);
+}
+
+// rows of `vecs` 16-byte vectors; grid-stride over (row, vec)
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const int32_t* __restrict__ index, uint4* __restrict__ dst,
+                                   int64_t rows, int64_t vecs) {
+  const int64_t total = rows * vecs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / vecs, c = i - r * vecs;
+    const int64_t s = index ? (int64_t)index[r] : r;
+    dst[i] = src[s * vecs + c];
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = from_f32<TD>(to_f32<TS>(src[i]));
+}
+
+__global__ void l2_normalize_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int64_t dim) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int64_t i = lane; i < dim; i += 32) { float v = x[r * dim + i]; s = fmaf(v, v, s); }
+  const float nrm = fmaxf(sqrtf(warp_sum(s)), 1e-12f);        // F.normalize: x / max(||x||, eps)
+  for (int64_t i = lane; i < dim; i += 32) y[r * dim + i] = x[r * dim + i] / nrm;
+}
+
+// images fp32 [B,3,S,S] -> patches [B*P, 768], column = c*256 + ky*16 + kx (Conv2d weight flatten order)
+template <typename T>
+__global__ void im2col16_kernel(const float* __restrict__ img, T* __restrict__ out, int64_t B, int S) {
+  const int G = S / 16;
+  const int64_t total = B * G * G * 192;          // one thread per 4 contiguous pixels (kx..kx+3)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % 192);
+    const int64_t pr = i / 192;                   // patch row index b*P + py*G + px
+    const int px = (int)(pr % G), py = (int)((pr / G) % G);
+    const int64_t b = pr / (G * G);
+    const int c = v / 64, ky = (v % 64) / 4, kx = (v % 4) * 4;
+    const float4 t = *reinterpret_cast<const float4*>(img + ((b * 3 + c) * S + (py * 16 + ky)) * (int64_t)S + px * 16 + kx);
+    T* o = out + pr * 768 + c * 256 + ky * 16 + kx;
+    o[0] = from_f32<T>(t.x); o[1] = from_f32<T>(t.y); o[2] = from_f32<T>(t.z); o[3] = from_f32<T>(t.w);
+  }
+}
+
+// x[b,0,:] = cls + pos[0]; x[b,1+p,:] = patch[b*P+p,:] + pos[1+p]   (src/vit.py:182-188); x fp32
+__global__ void vit_assemble_kernel(const float* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos,
+                                    float* __restrict__ x, int64_t B, int64_t N) {
+  const int64_t total = B * N * (D / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (D / 4)) * 4;
+    const int64_t r = i / (D / 4);
+    const int64_t n = r % N, b = r / N;
+    float4 a = (n == 0) ? *reinterpret_cast<const float4*>(cls + c)
+                        : *reinterpret_cast<const float4*>(patch + (b * (N - 1) + n - 1) * D + c);
+    const float4 p = *reinterpret_cast<const float4*>(pos + n * D + c);
+    *reinterpret_cast<float4*>(x + r * D + c) = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+  }
+}
+
+// feats[t] = cat(h0[t,0,:], h1[t,0,:]) (src/nlvr_encoder.py:909); h = [2][T*L][768]
+template <typename T>
+__global__ void gather_cls_kernel(const T* __restrict__ h, int64_t Tn, int64_t L, T* __restrict__ feats, float* __restrict__ feats_f32) {
+  const int64_t total = Tn * 2 * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % D);
+    const int s = (int)((i / D) % 2);
+    const int64_t t = i / (2 * D);
+    const T v = h[((int64_t)s * Tn * L + t * L) * D + c];
+    feats[i] = v;
+    if (feats_f32) feats_f32[i] = to_f32<T>(v);
+  }
+}
+
+// scores[t] = hidden[t,:] . w + b    (row 0 of cls_head.2, src/blip_stage2.py:53,136)
+__global__ void __launch_bounds__(WARPS * 32)
+head_dot_kernel(const float* __restrict__ hidden, const float* __restrict__ w, const float* __restrict__ b,
+                float* __restrict__ scores, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float hv[PER_LANE], wv[PER_LANE];
+  load24<float>(hidden + r * D + lane * PER_LANE, hv);
+  load24<float>(w + lane * PER_LANE, wv);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; i++) s = fmaf(hv[i], wv[i], s);
+  s = warp_sum(s);
+  if (lane == 0) scores[r] = s + b[0];
+}
+
+inline unsigned row_blocks(int64_t rows) { return (unsigned)((rows + WARPS - 1) / WARPS); }
+inline unsigned flat_blocks(int64_t n, int threads = 256) {
+  int64_t b = (n + threads - 1) / threads;
+  return (unsigned)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
+}
+
+}  // namespace
+
+extern "C" int cir_add_layernorm(cir_ctx* ctx, const void* x, int x_f32, int64_t x_rows, const void* res,
+                                 const float* gamma, const float* beta, int64_t rows_per_group,
+                                 void* y, int y_f32, int64_t rows, float eps) {
+  if (rows == 0) return CIR_OK;
+  CIR_CHECK_ARG(x && gamma && beta && y && x_rows > 0 && rows_per_group > 0, "add_layernorm: null/zero argument");
+  const bool f32 = ctx->dtype == CIR_DTYPE_F32;
+  dim3 grid(row_blocks(rows)), block(WARPS * 32);
+#define LN_LAUNCH(TX, TR, TY) \
+  add_layernorm_kernel<TX, TR, TY><<<grid, block, 0, ctx->stream>>>((const TX*)x, x_rows, (const TR*)res, gamma, beta, rows_per_group, (TY*)y, rows, eps)
+  if (f32) LN_LAUNCH(float, float, float);
+  else if (x_f32 && y_f32) LN_LAUNCH(float, bf16, float);
+  else if (x_f32) LN_LAUNCH(float, bf16, bf16);
+  else if (y_f32) LN_LAUNCH(bf16, bf16, float);
+  else LN_LAUNCH(bf16, bf16, bf16);
+#undef LN_LAUNCH
+  CIR_LAUNCH_CHECK(ctx);
+  return CIR_OK;
+}
+
+extern "C" int cir_bert_embeddings(cir_ctx* ctx, const int32_t* ids, int64_t Q, int64_t L, const float* word_emb,
+                                   const float* pos_emb, const float* gamma, const float* beta, void* out) {
+  const int64_t rows = Q * L;
+  if (rows == 0) return CIR_OK;
+  CIR_CHECK_ARG(L <= 512, "bert_embeddings: L=%lld exceeds max_position_embeddings 512", (long long)L);
+  if (ctx->dtype == CIR_DTYPE_F32)
+    bert_embeddings_kernel<float><<<row_blocks(rows), WARPS * 32, 0, ctx->stream>>>(ids, rows, L, word_emb, pos_emb, gamma, beta, (float*)out);
+  else
+    bert_embeddings_kernel<bf16><<<row_blocks(rows), WARPS * 32, 0, ctx->stream>>>(ids, rows, L, word_emb, pos_emb, gamma, beta, (bf16*)out);
+  CIR_LAUNCH_CHECK(ctx);
+  return CIR_OK;
+}
+
+extern "C" int cir_gather_rows(cir_ctx* ctx, const void* src, const int32_t* index, void* dst, int64_t rows, int64_t row_elems) {
+  if (rows == 0 || row_elems == 0) return CIR_OK;
+  const int64_t row_bytes = row_elems * (int64_t)act_size(ctx);
+  CIR_CHECK_ARG(row_bytes % 16 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "gather_rows: rows must be 16 B multiples and aligned");
+  const int64_t vecs = row_bytes / 16;
+  gather_rows_kernel<<<flat_blocks(rows * vecs), 256, 0, ctx->stream>>>((const uint4*)src, index, (uint4*)dst, rows, vecs);
+  CIR_LAUNCH_CHECK(ctx);
+  return CIR_OK;
+}
+
+extern "C" int cir_cast_f32_to_act(cir_ctx* ctx, const float* src, void* dst, int64_t n) {
+  if (n == 0) return CIR_OK;
+  if (ctx->dtype == CIR_DTYPE_F32) cast_kernel<float, float><<<flat_blocks(n), 256, 0, ctx->stream>>>(src, (float*)dst, n);
+  else cast_kernel<float, bf16><<<flat_blocks(n), 256, 0, ctx->stream>>>(src, (bf16*)dst, n);
+  CIR_LAUNCH_CHECK(ctx);
+  return CIR_OK;
+}
+
+extern "C" int cir_cast_act_to_f32(cir_ctx* ctx, const void* src, float* dst, int64_t n) {
+  if (n == 0) return CIR_OK;
+  if (ctx->dtype == CIR_DTYPE_F32) cast_kernel<float, float><<<flat_blocks(n), 256, 0, ctx->stream>>>((const float*)src, dst, n);
+  else cast_kernel<bf16, float><<<flat_blocks(n), 256, 0, ctx->stream>>>((const bf16*)src, dst, n);
+  CIR_LAUNCH_CHECK(ctx);
+  return CIR_OK;
+}
+
+extern "C" int cir_l2_normalize(cir_ctx* ctx, const float* x, float* y, int64_t rows, int64_t dim) {
+  if (rows == 0) return CIR_OK;
+  l2_normalize_kernel<<<row_blocks(rows), WARPS * 32, 0, ctx->stream>>>(x, y, rows, dim);
+  CIR_LAUNCH_CHECK(ctx);
+  return CIR_OK;
+}
+
+// ---- internal (pipeline.cu) -------------------------------------------------------------
+int cir_im2col16(cir_ctx* ctx, const float* img, void* out, int64_t B, int S) {
+  const int64_t n = B * (S / 16) * (S / 16) * 192;
+  if (ctx->dtype == CIR_DTYPE_F32) im2col16_kernel<float><<<flat_blocks(n), 256, 0, ctx->stream>>>(img, (float*)out, B, S);
+  else im2col16_kernel<bf16><<<flat_blocks(n), 256, 0, ctx->stream>>>(img, (bf16*)out, B, S);
+  CIR_LAUNCH_CHECK(ctx);
+  return CIR_OK;
+}
+int cir_vit_assemble(cir_ctx* ctx, const float* patch, const float* cls, const float* pos, float* x, int64_t B, int64_t N) {
+  vit_assemble_kernel<<<flat_blocks(B * N * (D / 4)), 256, 0, ctx->stream>>>(patch, cls, pos, x, B, N);
+  CIR_LAUNCH_CHECK(ctx);
+  return CIR_OK;
+}
+int cir_gather_cls(cir_ctx* ctx, const void* h, int64_t T, int64_t L, void* feats, float* feats_f32) {
+  if (T == 0) return CIR_OK;
+  if (ctx->dtype == CIR_DTYPE_F32) gather_cls_kernel<float><<<flat_blocks(T * 2 * D), 256, 0, ctx->stream>>>((const float*)h, T, L, (float*)feats, feats_f32);
+  else gather_cls_kernel<bf16><<<flat_blocks(T * 2 * D), 256, 0, ctx->stream>>>((const bf16*)h, T, L, (bf16*)feats, feats_f32);
+  CIR_LAUNCH_CHECK(ctx);
+  return CIR_OK;
+}
+int cir_head_dot(cir_ctx* ctx, const float* hidden, const float* w, const float* b, float* scores, int64_t rows) {
+  if (rows == 0) return CIR_OK;
+  head_dot_kernel<<<row_blocks(rows), WARPS * 32, 0, ctx->stream>>>(hidden, w, b, scores, rows);
+  CIR_LAUNCH_CHECK(ctx);
+  return CIR_OK;
+}

@@ -1,0 +1,422 @@
+"""Host-side engine: owns the native context, packs reference ``state_dict``s into the layouts
+``include/cir_b200.h`` documents, manages the workspace and drives the C-ABI pipelines.
+
+torch is used for device memory, streams and one-off weight layout preparation only; every
+arithmetic step of the hot path is a kernel in ``csrc/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import native as N
+from .schedule import plan_chunks
+
+HIDDEN, FFN, LAYERS, EMBED = 768, 3072, 12, 256
+NEG_FILL = -99999.99          # src/validate_stage2.py:123,258
+
+
+class Engine:
+    """One engine per (device, precision).  precision: "bf16" (tcgen05 tensor cores) or "fp32"
+    (the fp32 check mode of BASELINE.json: CUDA-core fp32 everywhere)."""
+
+    def __init__(self, device: Optional[torch.device | int | str] = None, precision: str = "bf16"):
+        if not torch.cuda.is_available():
+            raise N.CirError("no CUDA device: the B200 path has no CPU fallback")
+        assert precision in ("bf16", "fp32")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.precision = precision
+        self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self._lib = N.lib()
+        h = N.vp()
+        N.check(self._lib.cir_create(C.byref(h), dev.index, N.DTYPE_BF16 if precision == "bf16" else N.DTYPE_F32), "cir_create")
+        self.ctx = h
+        self._ws: Optional[torch.Tensor] = None
+        self.max_triplets = 2048
+        self.max_candidates = 48
+
+    # ------------------------------------------------------------------ plumbing
+    def _sync_stream(self):
+        N.check(self._lib.cir_set_stream(self.ctx, N.vp(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def set_gemm_impl(self, impl: int):
+        N.check(self._lib.cir_set_gemm_impl(self.ctx, impl), "cir_set_gemm_impl")
+
+    def launch_count(self, reset: bool = False) -> int:
+        return int(self._lib.cir_launch_count(self.ctx, 1 if reset else 0))
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def dev(self, t: torch.Tensor, dtype=None) -> torch.Tensor:
+        return t.to(device=self.device, dtype=dtype or t.dtype).contiguous()
+
+    def to_act(self, t: torch.Tensor) -> torch.Tensor:
+        """any float tensor -> contiguous device tensor in the activation dtype (cast by our kernel)."""
+        t = t.to(self.device)
+        if t.dtype == self.act_dtype:
+            return t.contiguous()
+        t = t.to(torch.float32).contiguous()
+        out = torch.empty(t.shape, dtype=self.act_dtype, device=self.device)
+        self._sync_stream()
+        N.check(self._lib.cir_cast_f32_to_act(self.ctx, N.ptr(t), N.ptr(out), t.numel()), "cast")
+        return out
+
+    def to_f32(self, t: torch.Tensor) -> torch.Tensor:
+        if t.dtype == torch.float32:
+            return t
+        out = torch.empty(t.shape, dtype=torch.float32, device=self.device)
+        self._sync_stream()
+        N.check(self._lib.cir_cast_act_to_f32(self.ctx, N.ptr(t.contiguous()), N.ptr(out), t.numel()), "cast")
+        return out
+
+    def _i32(self, a) -> torch.Tensor:
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=torch.int32).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.device, non_blocking=True)
+
+    # ------------------------------------------------------------------ weight packing
+    def _w(self, t: torch.Tensor) -> torch.Tensor:        # GEMM weight: activation dtype
+        return t.detach().to(device=self.device, dtype=torch.float32).to(self.act_dtype).contiguous()
+
+    def _p(self, t: torch.Tensor) -> torch.Tensor:        # bias / LN / tables: fp32
+        return t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+
+    def pack_vit(self, sd: Dict[str, torch.Tensor], prefix: str = "visual_encoder."):
+        keep: List[torch.Tensor] = []
+        w = N.VitWeights()
+
+        def W(name):
+            t = self._w(sd[prefix + name]); keep.append(t); return N.ptr(t)
+
+        def P(name, flat=False):
+            t = self._p(sd[prefix + name]);
+            keep.append(t); return N.ptr(t)
+        t = self._w(sd[prefix + "patch_embed.proj.weight"].reshape(HIDDEN, -1)); keep.append(t); w.patch_w = N.ptr(t)
+        w.patch_b = P("patch_embed.proj.bias")
+        t = self._p(sd[prefix + "cls_token"].reshape(-1)); keep.append(t); w.cls_token = N.ptr(t)
+        pos = self._p(sd[prefix + "pos_embed"].reshape(-1, HIDDEN)); keep.append(pos); w.pos_embed = N.ptr(pos)
+        for i in range(LAYERS):
+            b = f"blocks.{i}."
+            w.norm1_g[i] = P(b + "norm1.weight"); w.norm1_b[i] = P(b + "norm1.bias")
+            w.qkv_w[i] = W(b + "attn.qkv.weight"); w.qkv_b[i] = P(b + "attn.qkv.bias")
+            w.proj_w[i] = W(b + "attn.proj.weight"); w.proj_b[i] = P(b + "attn.proj.bias")
+            w.norm2_g[i] = P(b + "norm2.weight"); w.norm2_b[i] = P(b + "norm2.bias")
+            w.fc1_w[i] = W(b + "mlp.fc1.weight"); w.fc1_b[i] = P(b + "mlp.fc1.bias")
+            w.fc2_w[i] = W(b + "mlp.fc2.weight"); w.fc2_b[i] = P(b + "mlp.fc2.bias")
+        w.norm_g = P("norm.weight"); w.norm_b = P("norm.bias")
+        return w, keep, pos.shape[0]
+
+    def _cat_w(self, sd, names, keep, dim=0):
+        t = self._w(torch.cat([sd[n].float() for n in names], dim=dim)); keep.append(t); return N.ptr(t)
+
+    def _cat_p(self, sd, names, keep):
+        t = self._p(torch.cat([sd[n].float().reshape(-1) for n in names])); keep.append(t); return N.ptr(t)
+
+    def pack_stage1(self, sd: Dict[str, torch.Tensor]):
+        keep: List[torch.Tensor] = []
+        w = N.Stage1Weights()
+        e = "text_encoder.embeddings."
+        w.word_emb = self._cat_p(sd, [e + "word_embeddings.weight"], keep)
+        w.pos_emb = self._cat_p(sd, [e + "position_embeddings.weight"], keep)
+        w.emb_ln_g = self._cat_p(sd, [e + "LayerNorm.weight"], keep)
+        w.emb_ln_b = self._cat_p(sd, [e + "LayerNorm.bias"], keep)
+        for i in range(LAYERS):
+            p = f"text_encoder.encoder.layer.{i}."
+            a, c = p + "attention.", p + "crossattention."
+            w.self_qkv_w[i] = self._cat_w(sd, [a + f"self.{n}.weight" for n in ("query", "key", "value")], keep)
+            w.self_qkv_b[i] = self._cat_p(sd, [a + f"self.{n}.bias" for n in ("query", "key", "value")], keep)
+            w.self_out_w[i] = self._cat_w(sd, [a + "output.dense.weight"], keep)
+            w.self_out_b[i] = self._cat_p(sd, [a + "output.dense.bias"], keep)
+            w.self_ln_g[i] = self._cat_p(sd, [a + "output.LayerNorm.weight"], keep)
+            w.self_ln_b[i] = self._cat_p(sd, [a + "output.LayerNorm.bias"], keep)
+            w.cross_q_w[i] = self._cat_w(sd, [c + "self.query.weight"], keep)
+            w.cross_q_b[i] = self._cat_p(sd, [c + "self.query.bias"], keep)
+            w.cross_kv_w[i] = self._cat_w(sd, [c + "self.key.weight", c + "self.value.weight"], keep)
+            w.cross_kv_b[i] = self._cat_p(sd, [c + "self.key.bias", c + "self.value.bias"], keep)
+            w.cross_out_w[i] = self._cat_w(sd, [c + "output.dense.weight"], keep)
+            w.cross_out_b[i] = self._cat_p(sd, [c + "output.dense.bias"], keep)
+            w.cross_ln_g[i] = self._cat_p(sd, [c + "output.LayerNorm.weight"], keep)
+            w.cross_ln_b[i] = self._cat_p(sd, [c + "output.LayerNorm.bias"], keep)
+            w.ffn1_w[i] = self._cat_w(sd, [p + "intermediate.dense.weight"], keep)
+            w.ffn1_b[i] = self._cat_p(sd, [p + "intermediate.dense.bias"], keep)
+            w.ffn2_w[i] = self._cat_w(sd, [p + "output.dense.weight"], keep)
+            w.ffn2_b[i] = self._cat_p(sd, [p + "output.dense.bias"], keep)
+            w.ffn_ln_g[i] = self._cat_p(sd, [p + "output.LayerNorm.weight"], keep)
+            w.ffn_ln_b[i] = self._cat_p(sd, [p + "output.LayerNorm.bias"], keep)
+        w.text_proj_w = self._cat_w(sd, ["text_proj.weight"], keep)
+        w.text_proj_b = self._cat_p(sd, ["text_proj.bias"], keep)
+        w.vision_proj_w = self._cat_w(sd, ["vision_proj.weight"], keep)
+        w.vision_proj_b = self._cat_p(sd, ["vision_proj.bias"], keep)
+        return w, keep
+
+    def pack_stage2(self, sd: Dict[str, torch.Tensor]):
+        """Twin-stream packing; folds the avg / Linear merge of the cross-attention output into one
+        [768,1536] matrix per layer (src/nlvr_encoder.py:250-258), composed in float64."""
+        keep: List[torch.Tensor] = []
+        w = N.Stage2Weights()
+        e = "text_encoder.embeddings."
+        w.word_emb = self._cat_p(sd, [e + "word_embeddings.weight"], keep)
+        w.pos_emb = self._cat_p(sd, [e + "position_embeddings.weight"], keep)
+        w.emb_ln_g = self._cat_p(sd, [e + "LayerNorm.weight"], keep)
+        w.emb_ln_b = self._cat_p(sd, [e + "LayerNorm.bias"], keep)
+        for i in range(LAYERS):
+            p = f"text_encoder.encoder.layer.{i}."
+            a, c = p + "attention.", p + "crossattention."
+            w.self_qkv_w[i] = self._cat_w(sd, [a + f"self{s}.{n}.weight" for s in (0, 1) for n in ("query", "key", "value")], keep)
+            w.self_qkv_b[i] = self._cat_p(sd, [a + f"self{s}.{n}.bias" for s in (0, 1) for n in ("query", "key", "value")], keep)
+            w.self_out_w[i] = self._cat_w(sd, [a + "output.dense0.weight", a + "output.dense1.weight"], keep)
+            w.self_out_b[i] = self._cat_p(sd, [a + "output.dense0.bias", a + "output.dense1.bias"], keep)
+            w.self_ln_g[i] = self._cat_p(sd, [a + "output.LayerNormA.weight", a + "output.LayerNormB.weight"], keep)
+            w.self_ln_b[i] = self._cat_p(sd, [a + "output.LayerNormA.bias", a + "output.LayerNormB.bias"], keep)
+            w.cross_q_w[i] = self._cat_w(sd, [c + "self0.query.weight", c + "self1.query.weight"], keep)
+            w.cross_q_b[i] = self._cat_p(sd, [c + "self0.query.bias", c + "self1.query.bias"], keep)
+            w.cross_kv_w[i] = self._cat_w(sd, [c + "self0.key.weight", c + "self0.value.weight",
+                                               c + "self1.key.weight", c + "self1.value.weight"], keep)
+            w.cross_kv_b[i] = self._cat_p(sd, [c + "self0.key.bias", c + "self0.value.bias",
+                                               c + "self1.key.bias", c + "self1.value.bias"], keep)
+            W0, W1 = sd[c + "output.dense0.weight"].double(), sd[c + "output.dense1.weight"].double()
+            b0, b1 = sd[c + "output.dense0.bias"].double(), sd[c + "output.dense1.bias"].double()
+            if i >= 6:      # mergeMLP: merge_layer(cat[dense0(c0), dense1(c1)]), no activation (:252-254)
+                Wm, bm = sd[c + "output.merge_layer.weight"].double(), sd[c + "output.merge_layer.bias"].double()
+                Wa, Wb = Wm[:, :HIDDEN], Wm[:, HIDDEN:]
+                Wc = torch.cat([Wa @ W0, Wb @ W1], dim=1)
+                bc = Wa @ b0 + Wb @ b1 + bm
+            else:           # mergeAvg: (dense0(c0) + dense1(c1)) / 2 (:257-258)
+                Wc = 0.5 * torch.cat([W0, W1], dim=1)
+                bc = 0.5 * (b0 + b1)
+            t = self._w(Wc.float()); keep.append(t); w.cross_out_w[i] = N.ptr(t)
+            t = self._p(bc.float()); keep.append(t); w.cross_out_b[i] = N.ptr(t)
+            w.cross_ln_g[i] = self._cat_p(sd, [c + "output.LayerNormA.weight", c + "output.LayerNormB.weight"], keep)
+            w.cross_ln_b[i] = self._cat_p(sd, [c + "output.LayerNormA.bias", c + "output.LayerNormB.bias"], keep)
+            w.ffn1_w[i] = self._cat_w(sd, [p + "intermediate.dense.weight"], keep)
+            w.ffn1_b[i] = self._cat_p(sd, [p + "intermediate.dense.bias"], keep)
+            w.ffn2_w[i] = self._cat_w(sd, [p + "output.dense.weight"], keep)
+            w.ffn2_b[i] = self._cat_p(sd, [p + "output.dense.bias"], keep)
+            w.ffn_ln_g[i] = self._cat_p(sd, [p + "output.LayerNorm.weight"], keep)
+            w.ffn_ln_b[i] = self._cat_p(sd, [p + "output.LayerNorm.bias"], keep)
+        w.cls0_w = self._cat_w(sd, ["cls_head.0.weight"], keep)
+        w.cls0_b = self._cat_p(sd, ["cls_head.0.bias"], keep)
+        t = self._p(sd["cls_head.2.weight"][0]); keep.append(t); w.cls2_w = N.ptr(t)       # class-0 row only (:136)
+        t = self._p(sd["cls_head.2.bias"][0:1]); keep.append(t); w.cls2_b = N.ptr(t)
+        return w, keep
+
+    # ------------------------------------------------------------------ pipelines
+    def vit_forward(self, w, images: torch.Tensor, batch: int = 32) -> torch.Tensor:
+        """images fp32 [B,3,S,S] (host or device) -> tokens act [B,N,768]."""
+        assert images.dim() == 4 and images.shape[1] == 3 and images.shape[2] == images.shape[3]
+        B, S = images.shape[0], images.shape[2]
+        n_tok = (S // 16) ** 2 + 1
+        out = torch.empty(B, n_tok, HIDDEN, dtype=self.act_dtype, device=self.device)
+        self._sync_stream()
+        for b0 in range(0, B, batch):
+            img = images[b0:b0 + batch].to(self.device, torch.float32, non_blocking=True).contiguous()
+            nb = img.shape[0]
+            need = self._lib.cir_vit_workspace_bytes(self.ctx, nb, S)
+            ws = self.workspace(need)
+            N.check(self._lib.cir_vit_forward(self.ctx, C.byref(w), N.ptr(img), nb, S, N.ptr(out[b0:b0 + nb]),
+                                              N.ptr(ws), ws.numel()), "cir_vit_forward")
+        return out
+
+    def stage1_encode(self, w, gallery_tokens: torch.Tensor, ref_index, ids, mask, want_z=True, want_emb=True,
+                      normalize_twice=False, batch: int = 256):
+        """-> (z_t act [Q,L,768] | None, q_emb fp32 [Q,256] | None)"""
+        ref_index, ids, mask = self._i32(ref_index), self._i32(ids), self._i32(mask)
+        Q, L = ids.shape
+        n_tok = gallery_tokens.shape[1]
+        assert gallery_tokens.dtype == self.act_dtype and gallery_tokens.is_contiguous()
+        z = torch.empty(Q, L, HIDDEN, dtype=self.act_dtype, device=self.device) if want_z else None
+        emb = torch.empty(Q, EMBED, dtype=torch.float32, device=self.device) if want_emb else None
+        self._sync_stream()
+        for q0 in range(0, Q, batch):
+            nq = min(batch, Q - q0)
+            need = self._lib.cir_stage1_workspace_bytes(self.ctx, nq, L, n_tok)
+            ws = self.workspace(need)
+            N.check(self._lib.cir_stage1_encode(
+                self.ctx, C.byref(w), N.ptr(gallery_tokens), N.ptr(ref_index[q0:q0 + nq]), N.ptr(ids[q0:q0 + nq]),
+                N.ptr(mask[q0:q0 + nq]), nq, L, n_tok, N.ptr(z[q0:q0 + nq]) if want_z else N.vp(0),
+                N.ptr(emb[q0:q0 + nq]) if want_emb else N.vp(0), 1 if normalize_twice else 0, N.ptr(ws), ws.numel()),
+                "cir_stage1_encode")
+        return z, emb
+
+    def stage1_gallery_embed(self, w, tokens: torch.Tensor) -> torch.Tensor:
+        G, n_tok = tokens.shape[0], tokens.shape[1]
+        out = torch.empty(G, EMBED, dtype=torch.float32, device=self.device)
+        ws = self.workspace(G * EMBED * 4 + 512)
+        self._sync_stream()
+        N.check(self._lib.cir_stage1_gallery_embed(self.ctx, C.byref(w), N.ptr(tokens), G, n_tok, N.ptr(out), N.ptr(ws), ws.numel()),
+                "cir_stage1_gallery_embed")
+        return out
+
+    def stage2_score_chunk(self, w, gallery_tokens, cand_list, z_t, ids, mask, trip_query, trip_slot, want_feats=False):
+        """One C-ABI call: T triplets sharing C candidates -> (scores fp32 [T], feats fp32 [T,1536] | None)."""
+        cand_list, ids, mask = self._i32(cand_list), self._i32(ids), self._i32(mask)
+        trip_query, trip_slot = self._i32(trip_query), self._i32(trip_slot)
+        T, Cn, (Q, L), n_tok = trip_query.numel(), cand_list.numel(), ids.shape, gallery_tokens.shape[1]
+        assert z_t.shape == (Q, L, HIDDEN) and z_t.dtype == self.act_dtype and z_t.is_contiguous()
+        assert gallery_tokens.dtype == self.act_dtype and gallery_tokens.is_contiguous()
+        scores = torch.empty(T, dtype=torch.float32, device=self.device)
+        feats = torch.empty(T, 2 * HIDDEN, dtype=torch.float32, device=self.device) if want_feats else None
+        need = self._lib.cir_stage2_workspace_bytes(self.ctx, T, Cn, Q, L, n_tok)
+        ws = self.workspace(need)
+        self._sync_stream()
+        N.check(self._lib.cir_stage2_score(
+            self.ctx, C.byref(w), N.ptr(gallery_tokens), N.ptr(cand_list), Cn, N.ptr(z_t), N.ptr(ids), N.ptr(mask),
+            Q, L, n_tok, N.ptr(trip_query), N.ptr(trip_slot), T, N.ptr(scores), N.ptr(feats), N.ptr(ws), ws.numel()),
+            "cir_stage2_score")
+        return scores, feats
+
+    def stage2_score_matrix(self, w, gallery_tokens, z_t, ids, mask, cand_idx, row_active=None):
+        """All Q*K triplets, candidate-major.  z_t act [Q,L,768]; ids/mask [Q,L]; cand_idx [Q,K] ->
+        scores fp32 [Q,K]; inactive rows are filled with -99999.99 (src/validate_stage2.py:123,258)."""
+        cand_np = cand_idx.cpu().numpy() if isinstance(cand_idx, torch.Tensor) else np.asarray(cand_idx)
+        Q, K = cand_np.shape
+        act_np = None if row_active is None else np.asarray(row_active, dtype=bool)
+        chunks = plan_chunks(cand_np, act_np, self.max_triplets, self.max_candidates)
+        out = torch.full((Q * K,), NEG_FILL, dtype=torch.float32, device=self.device)
+        ids_d, mask_d = self._i32(ids), self._i32(mask)
+        for ch in chunks:
+            ql = torch.from_numpy(ch.query_list.astype(np.int64)).to(self.device)
+            s, _ = self.stage2_score_chunk(w, gallery_tokens, ch.cand_list, z_t.index_select(0, ql).contiguous(),
+                                           ids_d.index_select(0, ql), mask_d.index_select(0, ql), ch.trip_query, ch.trip_slot)
+            out.index_copy_(0, torch.from_numpy(ch.flat_pos).to(self.device), s)
+        return out.view(Q, K)
+
+    # ------------------------------------------------------------------ sort / top-K / recall
+    def rerank_sort(self, scores: torch.Tensor) -> torch.Tensor:
+        scores = scores.to(self.device, torch.float32).contiguous()
+        Q, K = scores.shape
+        order = torch.empty(Q, K, dtype=torch.int32, device=self.device)
+        self._sync_stream()
+        N.check(self._lib.cir_rerank_sort(self.ctx, N.ptr(scores), Q, K, N.ptr(order)), "cir_rerank_sort")
+        return order
+
+    def topk_from_dist(self, dist: torch.Tensor, k: int, exclude=None, col_offset: int = 0):
+        dist = dist.to(self.device, torch.float32).contiguous()
+        Q, G = dist.shape
+        td = torch.empty(Q, k, dtype=torch.float32, device=self.device)
+        ti = torch.empty(Q, k, dtype=torch.int32, device=self.device)
+        ex = None if exclude is None else self._i32(exclude)
+        ws = self.workspace(self._lib.cir_topk_workspace_bytes(Q, G, k))
+        self._sync_stream()
+        N.check(self._lib.cir_topk_from_dist(self.ctx, N.ptr(dist), Q, G, G, N.ptr(ex), col_offset, k, N.ptr(td), N.ptr(ti),
+                                             N.ptr(ws), ws.numel()), "cir_topk_from_dist")
+        return td, ti
+
+    def stage1_topk(self, q_emb: torch.Tensor, g_emb: torch.Tensor, k: int, exclude=None, col_offset: int = 0):
+        q_emb = q_emb.to(self.device, torch.float32).contiguous()
+        g_emb = g_emb.to(self.device, torch.float32).contiguous()
+        Q, G = q_emb.shape[0], g_emb.shape[0]
+        td = torch.empty(Q, k, dtype=torch.float32, device=self.device)
+        ti = torch.empty(Q, k, dtype=torch.int32, device=self.device)
+        ex = None if exclude is None else self._i32(exclude)
+        ws = self.workspace(self._lib.cir_stage1_topk_workspace_bytes(Q, G, k))
+        self._sync_stream()
+        N.check(self._lib.cir_stage1_topk(self.ctx, N.ptr(q_emb), N.ptr(g_emb), Q, G, N.ptr(ex), col_offset, k, N.ptr(td),
+                                          N.ptr(ti), N.ptr(ws), ws.numel()), "cir_stage1_topk")
+        return td, ti
+
+    def topk_merge(self, dist_in: torch.Tensor, idx_in: torch.Tensor):
+        """dist_in/idx_in [P,Q,K] (per-shard sorted lists) -> merged (dist [Q,K], idx [Q,K])."""
+        P, Q, K = dist_in.shape
+        dist_in = dist_in.to(self.device, torch.float32).contiguous()
+        idx_in = idx_in.to(self.device, torch.int32).contiguous()
+        td = torch.empty(Q, K, dtype=torch.float32, device=self.device)
+        ti = torch.empty(Q, K, dtype=torch.int32, device=self.device)
+        ws = self.workspace(self._lib.cir_topk_workspace_bytes(Q, 0, K))
+        self._sync_stream()
+        N.check(self._lib.cir_topk_merge(self.ctx, N.ptr(dist_in), N.ptr(idx_in), P, Q, K, N.ptr(td), N.ptr(ti), N.ptr(ws), ws.numel()),
+                "cir_topk_merge")
+        return td, ti
+
+    def recall_counts(self, labels: torch.Tensor, order: torch.Tensor, ks: Sequence[int]) -> List[int]:
+        labels = labels.to(self.device).to(torch.uint8).contiguous()
+        order = order.to(self.device, torch.int32).contiguous()
+        Q, K = labels.shape
+        hits = torch.zeros(len(ks), dtype=torch.int64, device=self.device)
+        arr = (N.i32 * len(ks))(*[int(k) for k in ks])
+        self._sync_stream()
+        N.check(self._lib.cir_recall_counts(self.ctx, N.ptr(labels), N.ptr(order), Q, K, arr, len(ks), N.ptr(hits)), "cir_recall_counts")
+        return hits.cpu().tolist()
+
+    # ------------------------------------------------------------------ primitive ops (tests)
+    def gemm(self, A, W, bias=None, residual=None, act=N.ACT_NONE, out_f32=False):
+        """A [B?,M,K], W [B?,N,K] in act dtype -> C; thin test hook over cir_gemm."""
+        batched = A.dim() == 3
+        A3 = A if batched else A[None]
+        W3 = W if W.dim() == 3 else W[None]
+        Bn, M, K = A3.shape
+        Nn = W3.shape[1]
+        assert A3.dtype == self.act_dtype and W3.dtype == self.act_dtype
+        A3, W3 = A3.contiguous(), W3.contiguous()
+        c_dtype = torch.float32 if (out_f32 or self.precision == "fp32") else self.act_dtype
+        Cm = torch.empty(Bn, M, Nn, dtype=c_dtype, device=self.device)
+        g = N.GemmArgs()
+        g.A, g.W, g.C = N.ptr(A3), N.ptr(W3), N.ptr(Cm)
+        if bias is not None:
+            bias = bias.to(self.device, torch.float32).contiguous().view(Bn, Nn)
+        g.bias = N.ptr(bias)
+        if residual is not None:
+            residual = residual.contiguous().view(Bn, M, Nn)
+        g.residual = N.ptr(residual)
+        g.M, g.N, g.K = M, Nn, K
+        g.lda, g.ldw, g.ldc, g.ldres = K, K, Nn, Nn
+        g.a_bstride, g.w_bstride, g.c_bstride, g.bias_bstride, g.res_bstride = M * K, Nn * K, M * Nn, Nn, M * Nn
+        g.batch, g.act = Bn, act
+        g.c_f32 = 1 if c_dtype == torch.float32 else 0
+        g.res_f32 = 1 if (residual is not None and residual.dtype == torch.float32) else 0
+        self._sync_stream()
+        N.check(self._lib.cir_gemm(self.ctx, C.byref(g)), "cir_gemm")
+        return Cm if batched else Cm[0]
+
+    def attention(self, q, k, v, key_mask=None, kv_index=None, scale=0.125):
+        """q [B,Lq,H*64], k/v [Bk,Lk,H*64] act dtype -> o [B,Lq,H*64]; test hook over cir_attention."""
+        B, Lq, HD = q.shape
+        Lk = k.shape[1]
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        o = torch.empty_like(q)
+        a = N.AttnArgs()
+        a.q, a.k, a.v, a.o = N.ptr(q), N.ptr(k), N.ptr(v), N.ptr(o)
+        a.q_bs, a.q_rs, a.o_bs, a.o_rs = Lq * HD, HD, Lq * HD, HD
+        a.k_bs, a.k_rs, a.v_bs, a.v_rs = Lk * HD, HD, Lk * HD, HD
+        km = None if key_mask is None else self._i32(key_mask)
+        ki = None if kv_index is None else self._i32(kv_index)
+        a.key_mask, a.kv_index, a.mask_index = N.ptr(km), N.ptr(ki), N.vp(0)
+        a.B, a.H, a.Lq, a.Lk, a.scale = B, HD // 64, Lq, Lk, scale
+        self._sync_stream()
+        N.check(self._lib.cir_attention(self.ctx, C.byref(a)), "cir_attention")
+        return o
+
+    def add_layernorm(self, x, gamma, beta, res=None, x_rows=None, rows_per_group=None, eps=1e-12, out_f32=False):
+        rows = (res.shape[0] if res is not None else x.shape[0])
+        x = x.contiguous()
+        y = torch.empty(rows, HIDDEN, dtype=torch.float32 if (out_f32 or self.precision == "fp32") else self.act_dtype, device=self.device)
+        self._sync_stream()
+        N.check(self._lib.cir_add_layernorm(
+            self.ctx, N.ptr(x), 1 if x.dtype == torch.float32 else 0, x_rows or x.shape[0], N.ptr(res.contiguous() if res is not None else None),
+            N.ptr(gamma.float().contiguous()), N.ptr(beta.float().contiguous()), rows_per_group or rows, N.ptr(y),
+            1 if y.dtype == torch.float32 else 0, rows, eps), "cir_add_layernorm")
+        return y
+
+
+_engines: Dict[Tuple[int, str], Engine] = {}
+
+
+def get_engine(device=None, precision: str = "bf16") -> Engine:
+    """Process-wide engine cache (one per device and precision)."""
+    if not torch.cuda.is_available():
+        raise N.CirError("no CUDA device: the B200 path has no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else (torch.device(device).index or torch.cuda.current_device())
+    key = (idx, precision)
+    if key not in _engines:
+        _engines[key] = Engine(torch.device("cuda", idx), precision)
+    return _engines[key]

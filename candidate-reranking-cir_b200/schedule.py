@@ -1,0 +1,91 @@
+"""Candidate-major triplet scheduling (pure numpy host logic, no GPU needed).
+
+The reference scores one query at a time (src/validate_stage2.py:94-125,235-275) and therefore
+recomputes the cross-attention K/V projections of a gallery image for every top-K list that
+names it (src/nlvr_encoder.py:158-159: 69 % of its FLOPs).  Triplets are independent
+(src/blip_stage2.py:118-136), so here the Q*K (query, candidate) pairs are sorted by candidate
+and cut into chunks; inside a chunk every unique candidate's K/V is computed once.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterator, List, Optional
+
+import numpy as np
+
+
+@dataclass
+class Chunk:
+    flat_pos: np.ndarray     # [T] int64  position q*K+k of each triplet in the [Q,K] score matrix
+    cand_list: np.ndarray    # [C] int32  unique gallery rows of the chunk (ascending)
+    trip_slot: np.ndarray    # [T] int32  index into cand_list
+    query_list: np.ndarray   # [Qc] int32 unique query rows of the chunk (ascending)
+    trip_query: np.ndarray   # [T] int32  index into query_list
+
+
+def plan_chunks(cand_idx: np.ndarray, row_active: Optional[np.ndarray] = None, max_triplets: int = 2048,
+                max_candidates: int = 64) -> List[Chunk]:
+    """cand_idx [Q,K] int -> chunks covering every triplet of the active rows exactly once.
+
+    A chunk holds at most ``max_triplets`` triplets and ``max_candidates`` unique candidates; all
+    triplets of one candidate are kept together unless a single candidate has more than
+    ``max_triplets`` of them (then it is split, recomputing its K/V once per piece)."""
+    cand_idx = np.asarray(cand_idx)
+    assert cand_idx.ndim == 2
+    Q, K = cand_idx.shape
+    assert max_triplets >= 1 and max_candidates >= 1
+    flat = np.arange(Q * K, dtype=np.int64)
+    if row_active is not None:
+        row_active = np.asarray(row_active, dtype=bool)
+        assert row_active.shape == (Q,)
+        flat = flat[np.repeat(row_active, K)]
+    if flat.size == 0:
+        return []
+    cands = cand_idx.reshape(-1)[flat].astype(np.int64)
+    assert cands.min() >= 0, "negative candidate index"
+    order = np.argsort(cands, kind="stable")
+    flat, cands = flat[order], cands[order]
+    # run boundaries of equal candidates
+    starts = np.flatnonzero(np.r_[True, cands[1:] != cands[:-1]])
+    ends = np.r_[starts[1:], cands.size]
+    chunks: List[Chunk] = []
+    cur_lo = 0          # first triplet of the open chunk
+    cur_hi = 0
+    cur_c = 0
+    def close(lo, hi):
+        if hi > lo:
+            chunks.append(_make_chunk(flat[lo:hi], cands[lo:hi], K))
+    for s, e in zip(starts, ends):
+        n = e - s
+        if n > max_triplets:                      # oversized candidate: flush, then split it alone
+            close(cur_lo, cur_hi)
+            for p in range(s, e, max_triplets):
+                close(p, min(p + max_triplets, e))
+            cur_lo = cur_hi = e
+            cur_c = 0
+            continue
+        if (cur_hi - cur_lo) + n > max_triplets or cur_c + 1 > max_candidates:
+            close(cur_lo, cur_hi)
+            cur_lo = s
+            cur_c = 0
+        cur_hi = e
+        cur_c += 1
+    close(cur_lo, cur_hi)
+    return chunks
+
+
+def _make_chunk(flat_pos: np.ndarray, cands: np.ndarray, K: int) -> Chunk:
+    cand_list, trip_slot = np.unique(cands, return_inverse=True)
+    queries = flat_pos // K
+    query_list, trip_query = np.unique(queries, return_inverse=True)
+    return Chunk(flat_pos=flat_pos.astype(np.int64), cand_list=cand_list.astype(np.int32),
+                 trip_slot=trip_slot.astype(np.int32), query_list=query_list.astype(np.int32),
+                 trip_query=trip_query.astype(np.int32))
+
+
+def shard_rows(num_rows: int, rank: int, world: int) -> slice:
+    """Contiguous block partition of ``num_rows`` units over ``world`` ranks (first ranks get the
+    remainder).  Used for queries (stage II) and gallery rows (stage I)."""
+    base, rem = divmod(num_rows, world)
+    lo = rank * base + min(rank, rem)
+    return slice(lo, lo + base + (1 if rank < rem else 0))

@@ -256,3 +256,51 @@ def make_random_topk(num_queries: int, gallery: int, k: int, ref_idx: torch.Tens
         cand[q] = row.to(torch.int32)
     labels = cand.to(torch.int64) == target_idx[:, None]
     return cand, labels
+
+
+class SyntheticRelativeDataset:
+    """Dataset-free stand-in for ``CIRRDataset``/``FashionIQDataset`` in 'relative' mode with a loaded
+    top-K file (src/data_utils.py:166-179,290-305).  Exposes what the metric functions read:
+    ``K``, ``K_labels`` (numpy bool [Q,K]), ``split``/``dress_types`` plus per-query arrays:
+    ``reference_names``, ``target_names``, ``captions`` (str or [str,str] for Fashion-IQ),
+    ``K_sorted_index_names`` [Q,K], and for CIRR ``group_members`` [Q,6] (reference first)."""
+
+    def __init__(self, index_names, ref_idx, target_idx, captions, cand_idx, kind="cirr", group_idx=None,
+                 split="val", dress_types=("dress",), token_batch=None):
+        import numpy as np
+        self.kind = kind
+        self.split = split
+        self.dress_types = list(dress_types)
+        self.index_names = list(index_names)
+        names = np.array(self.index_names)
+        self.reference_names = names[np.asarray(ref_idx)].tolist()
+        self.target_names = names[np.asarray(target_idx)].tolist()
+        self.captions = list(captions)
+        cand_idx = np.asarray(cand_idx)
+        self.K = cand_idx.shape[1]
+        self.K_sorted_index_names = names[cand_idx]
+        self.K_labels = self.K_sorted_index_names == np.array(self.target_names)[:, None]
+        self.group_members = None if group_idx is None else names[np.asarray(group_idx)]
+        self.token_batch = token_batch      # optional pre-tokenised captions (TokenBatch)
+
+    def __len__(self):
+        return len(self.reference_names)
+
+
+def index_names_for(n: int) -> List[str]:
+    return [f"img_{i:07d}" for i in range(n)]
+
+
+def make_group_members(ref_idx: torch.Tensor, target_idx: torch.Tensor, gallery: int, seed: int = 5) -> torch.Tensor:
+    """CIRR 'img_set' members: [Q,6] = reference, target and 4 other distinct images."""
+    g = torch.Generator().manual_seed(seed)
+    Q = ref_idx.numel()
+    out = torch.empty(Q, 6, dtype=torch.int64)
+    for q in range(Q):
+        r, t = int(ref_idx[q]), int(target_idx[q])
+        perm = torch.randperm(gallery, generator=g)
+        others = [int(x) for x in perm if int(x) not in (r, t)][:4]
+        row = [t] + others
+        order = torch.randperm(5, generator=g).tolist()
+        out[q] = torch.tensor([r] + [row[i] for i in order])
+    return out

@@ -1,0 +1,104 @@
+"""Stage-II evaluation drivers with the reference's function surface (src/validate_stage2.py:33-298),
+restructured for the GPU: instead of a Python loop issuing one query at a time
+(src/validate_stage2.py:94-125,235-275) all queries' z_t are computed in batches, all Q*K triplets
+are scored candidate-major, and the re-sort + recall counting run as kernels."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+from .blip import tokenize
+from .engine import NEG_FILL
+
+
+def _name_index(index_names):
+    return {n: i for i, n in enumerate(index_names)}
+
+
+def _percent(count: int, total: int) -> float:
+    # (torch.sum(labels[:, :k]) / len(labels)).item() * 100   (src/validate_stage2.py:60-62,196-203)
+    return (torch.tensor(int(count)) / total).item() * 100
+
+
+def _fiq_captions(captions) -> List[str]:
+    # src/validate_stage2.py:97-100
+    out = []
+    for c in captions:
+        if isinstance(c, (list, tuple)) and len(c) == 2:
+            out.append(f"{c[0].strip('.?, ').capitalize()} and {c[1].strip('.?, ')}")
+        else:
+            out.append(c)
+    return out
+
+
+def _tokens(blip_model, dataset, captions):
+    tb = getattr(dataset, "token_batch", None)
+    return tokenize(blip_model.tokenizer, tb if tb is not None else captions, blip_model.engine.device)
+
+
+def _predict(blip_model, model_stage1, dataset, index_names, index_features, captions, cand_names, row_active):
+    eng = blip_model.engine
+    n2i = _name_index(index_names)
+    ref_idx = np.array([n2i[n] for n in dataset.reference_names], dtype=np.int32)
+    cand_idx = np.vectorize(n2i.__getitem__, otypes=[np.int32])(np.asarray(cand_names))
+    ids, mask = _tokens(blip_model, dataset, captions)
+    gallery = eng.to_act(index_features)
+    # z_t from the frozen stage-I encoder on the reference image's tokens (src/validate_stage2.py:105-106,243-244)
+    z_t, _ = model_stage1.encode_queries(gallery, ref_idx, ids, mask, want_z=True, want_emb=False)
+    return blip_model.score_triplets(z_t, ids, mask, gallery, cand_idx, row_active), z_t, ids, mask, gallery, n2i
+
+
+def generate_fiq_val_predictions(blip_model, model_stage1, relative_val_dataset, index_names, index_features):
+    """src/validate_stage2.py:69-129 -> (predicted_logits [Q,K] fp32 on device, target_names)."""
+    caps = _fiq_captions(relative_val_dataset.captions)
+    active = np.asarray(relative_val_dataset.K_labels).any(axis=1)                  # `if True in K_labels` (:95)
+    logits, *_ = _predict(blip_model, model_stage1, relative_val_dataset, index_names, index_features, caps,
+                          relative_val_dataset.K_sorted_index_names, active)
+    return logits, list(relative_val_dataset.target_names)
+
+
+def compute_fiq_val_metrics(relative_val_dataset, blip_model, model_stage1, index_features, index_names) -> Tuple[float, float]:
+    """src/validate_stage2.py:33-66 -> (recall@10, recall@50)."""
+    predicted_logits, _ = generate_fiq_val_predictions(blip_model, model_stage1, relative_val_dataset, index_names, index_features)
+    eng = blip_model.engine
+    order = eng.rerank_sort(predicted_logits)                                       # argsort descending (:53)
+    labels = torch.from_numpy(np.asarray(relative_val_dataset.K_labels))
+    h10, h50 = eng.recall_counts(labels, order, (10, 50))                           # take_along_axis + sums (:56-61)
+    Q = len(labels)
+    return _percent(h10, Q), _percent(h50, Q)
+
+
+def generate_cirr_val_predictions(blip_model, model_stage1, relative_val_dataset, index_names, index_features):
+    """src/validate_stage2.py:209-278 -> (predicted_logits [Q,K], group_predicted_logits [Q,5],
+    reference_names, target_names, group_members_noRef)."""
+    ds = relative_val_dataset
+    active = np.asarray(ds.K_labels).any(axis=1)                                    # `if True in K_labels` (:239)
+    logits, z_t, ids, mask, gallery, n2i = _predict(blip_model, model_stage1, ds, index_names, index_features,
+                                                     list(ds.captions), ds.K_sorted_index_names, active)
+    # group members without the reference image, scored for EVERY query (:260-269)
+    gm = np.asarray(ds.group_members)
+    refs = np.asarray(ds.reference_names)
+    group_noref = [[m for m in row if m != r] for row, r in zip(gm.tolist(), refs.tolist())]
+    assert all(len(g) == 5 for g in group_noref)
+    gidx = np.vectorize(n2i.__getitem__, otypes=[np.int32])(np.asarray(group_noref))
+    group_logits = blip_model.score_triplets(z_t, ids, mask, gallery, gidx, None)
+    return logits, group_logits, list(ds.reference_names), list(ds.target_names), group_noref
+
+
+def compute_cirr_val_metrics(relative_val_dataset, blip_model, model_stage1, index_features, index_names):
+    """src/validate_stage2.py:153-206 -> (group_recall@1,2,3, recall@1,5,10,50)."""
+    predicted_logits, group_logits, _, target_names, group_members = generate_cirr_val_predictions(
+        blip_model, model_stage1, relative_val_dataset, index_names, index_features)
+    eng = blip_model.engine
+    order = eng.rerank_sort(predicted_logits)                                       # :174
+    labels = torch.from_numpy(np.asarray(relative_val_dataset.K_labels))            # :178
+    r1, r5, r10, r50 = eng.recall_counts(labels, order, (1, 5, 10, 50))
+    group_members = np.array(group_members)
+    assert group_members.shape[1] == 5                                              # :187
+    gorder = eng.rerank_sort(group_logits)                                          # :190
+    glabels = torch.from_numpy(group_members == np.array(target_names)[:, None])    # :192-193 (before sorting; gathered by recall_counts)
+    g1, g2, g3 = eng.recall_counts(glabels, gorder, (1, 2, 3))
+    Q = len(labels)
+    return (_percent(g1, Q), _percent(g2, Q), _percent(g3, Q), _percent(r1, Q), _percent(r5, Q), _percent(r10, Q), _percent(r50, Q))

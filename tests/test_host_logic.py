@@ -1,0 +1,101 @@
+"""CPU tests of the host side: C-ABI library exports, scheduler, tokenizer, synthetic data."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import cir_b200 as cir
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from importlib import import_module
+    native = import_module("candidate-reranking-cir_b200.native")
+    hdr = open(os.path.join(ROOT, "include", "cir_b200.h")).read()
+    declared = set(re.findall(r"\b(cir_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    assert os.path.exists(native.LIB_PATH), "build the library first: python __graft_entry__.py"
+    lib = ctypes.CDLL(native.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/cir_b200.h but not exported"
+    assert declared == set(native.exported_symbols()), declared ^ set(native.exported_symbols())
+    assert native.lib().cir_version() == 100
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from importlib import import_module
+    native = import_module("candidate-reranking-cir_b200.native")
+    engine = import_module("candidate-reranking-cir_b200.engine")
+    with pytest.raises(native.CirError):
+        engine.get_engine()
+    with pytest.raises(native.CirError):
+        cir.blip_stage2.BLIP_NLVR(image_size=384)
+
+
+def test_plan_chunks_covers_every_triplet_once():
+    from importlib import import_module
+    sched = import_module("candidate-reranking-cir_b200.schedule")
+    rng = np.random.default_rng(0)
+    Q, K, G = 37, 11, 23
+    cand = np.stack([rng.permutation(G)[:K] for _ in range(Q)]).astype(np.int32)
+    active = rng.random(Q) < 0.8
+    for mt, mc in ((2048, 64), (16, 3), (5, 1), (1, 1)):
+        chunks = sched.plan_chunks(cand, active, mt, mc)
+        seen = np.concatenate([c.flat_pos for c in chunks]) if chunks else np.zeros(0, np.int64)
+        want = np.flatnonzero(np.repeat(active, K))
+        assert np.array_equal(np.sort(seen), want)
+        for c in chunks:
+            assert len(c.flat_pos) <= mt and len(c.cand_list) <= mc
+            assert np.array_equal(c.cand_list[c.trip_slot], cand.reshape(-1)[c.flat_pos])
+            assert np.array_equal(c.query_list[c.trip_query], c.flat_pos // K)
+            assert np.all(np.diff(c.cand_list) > 0)
+    assert sched.plan_chunks(cand, np.zeros(Q, bool)) == []
+    assert sched.plan_chunks(np.zeros((0, 4), np.int32)) == []
+
+
+def test_plan_chunks_splits_an_oversized_candidate():
+    from importlib import import_module
+    sched = import_module("candidate-reranking-cir_b200.schedule")
+    cand = np.zeros((10, 3), np.int32)         # one candidate, 30 triplets
+    chunks = sched.plan_chunks(cand, None, max_triplets=8, max_candidates=4)
+    assert [len(c.flat_pos) for c in chunks] == [8, 8, 8, 6]
+    assert all(list(c.cand_list) == [0] for c in chunks)
+
+
+def test_shard_rows_partitions():
+    from importlib import import_module
+    sched = import_module("candidate-reranking-cir_b200.schedule")
+    for n in (0, 1, 7, 8, 4181):
+        for w in (1, 2, 3, 8):
+            got = [sched.shard_rows(n, r, w) for r in range(w)]
+            assert got[0].start == 0 and got[-1].stop == n
+            assert all(a.stop == b.start for a, b in zip(got, got[1:]))
+            sizes = [s.stop - s.start for s in got]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synthetic_tokenizer_surface():
+    tok = cir.synthetic.SyntheticTokenizer()
+    enc = tok(["make the dog bigger", "a"], padding="longest", return_tensors="pt")
+    assert enc.input_ids.shape == enc.attention_mask.shape == (2, 6)
+    assert enc.input_ids[0, 0] == 101 and enc.input_ids[0, -1] == 102
+    assert enc.attention_mask[1].tolist() == [1, 1, 1, 0, 0, 0]
+    assert tok.enc_token_id == 30523
+    again = tok(["make the dog bigger"])
+    assert torch.equal(again.input_ids[0], enc.input_ids[0])
+
+
+def test_random_topk_plants_targets():
+    syn = cir.synthetic
+    ref, tgt, ids, mask = syn.make_queries(50, 40, 8)
+    cand, labels = syn.make_random_topk(50, 40, 10, ref, tgt, hit_rate=0.9)
+    assert cand.shape == (50, 10) and labels.sum(1).max() <= 1
+    assert not (cand.long() == ref[:, None]).any()
+    assert all(len(set(r.tolist())) == 10 for r in cand)
+    assert 0.7 < labels.any(1).float().mean() <= 1.0

@@ -1,0 +1,65 @@
+"""Quick on-box performance probe (not a bench): GEMM TF/s at the path's shapes, attention time,
+stage-II chunk throughput.  Prints one line per measurement."""
+import sys, os, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import cir_b200 as cir
+
+N_ = cir.native
+e = cir.engine.get_engine(precision="bf16")
+
+
+def timeit(fn, warm=2, it=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(it):
+        fn()
+    t.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(t) / it
+
+
+def gemm_probe():
+    for (M, Nn, K, b, act) in [(8192, 8192, 8192, 1, 0), (65536, 768, 768, 2, 0), (65536, 2304, 768, 2, 0), (36928, 3072, 768, 1, 0),
+                               (131072, 3072, 768, 1, 1), (131072, 768, 3072, 1, 0), (65536, 768, 1536, 1, 0), (4096, 768, 768, 2, 0)]:
+        A = torch.randn(b, M, K, device="cuda").bfloat16()
+        W = (torch.randn(b, Nn, K, device="cuda") * 0.05).bfloat16()
+        bias = torch.randn(b, Nn, device="cuda")
+        ms = timeit(lambda: e.gemm(A, W, bias, act=act))
+        tf = 2.0 * M * Nn * K * b / ms / 1e9
+        ms_t = timeit(lambda: torch.matmul(A, W.transpose(1, 2)))
+        tf_t = 2.0 * M * Nn * K * b / ms_t / 1e9
+        print(f"gemm M={M} N={Nn} K={K} batch={b} act={act}: {ms:.3f} ms {tf:.0f} TF/s | cuBLAS {ms_t:.3f} ms {tf_t:.0f} TF/s", flush=True)
+        del A, W
+
+
+def stage2_probe(T_per=2048, C=48, L=32, reps=3):
+    syn = cir.synthetic
+    sd2 = syn.make_stage2_state_dict(0, 384, "reference")
+    m2 = cir.blip_stage2.blip_stage2(image_size=384, state_dict=sd2, precision="bf16")
+    G = 256
+    tokens = torch.randn(G, 577, 768, device="cuda").bfloat16()
+    Q = 512
+    K = 50
+    ids, mask = syn.make_token_ids(Q, L, seed=2)
+    ids[:, 0] = 30523
+    z_t = torch.randn(Q, L, 768, device="cuda").bfloat16()
+    g = torch.Generator().manual_seed(0)
+    cand = torch.stack([torch.randperm(G, generator=g)[:K] for _ in range(Q)]).int().numpy()
+    for (mt, mc) in ((1024, 32), (2048, 48), (4096, 64), (8192, 128)):
+        m2.engine.max_triplets, m2.engine.max_candidates = mt, mc
+        e.launch_count(reset=True)
+        ms = timeit(lambda: m2.score_triplets(z_t, ids, mask, tokens, cand), warm=1, it=reps)
+        nl = e.launch_count() / (reps + 1)
+        print(f"stage2 Q={Q} K={K} L={L} G={G} chunk(T<={mt},C<={mc}): {ms:.1f} ms -> {Q*K/ms*1e3:.0f} triplets/s, {nl:.0f} launches/pass", flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gemm", "stage2"]
+    if "gemm" in which:
+        gemm_probe()
+    if "stage2" in which:
+        stage2_probe()
