@@ -93,5 +93,5 @@ def run(name, *, seed, style, G, Q, K, L, min_len, head_gain):
 
 
 if __name__ == "__main__":
-    run("pipeline_small.npz", seed=0, style="dense", G=6, Q=3, K=4, L=12, min_len=8, head_gain=2.0)
+    run("pipeline_small.npz", seed=0, style="dense", G=6, Q=3, K=4, L=12, min_len=8, head_gain=1.0)
     run("stage2_L32.npz", seed=1, style="reference", G=4, Q=1, K=3, L=32, min_len=None, head_gain=1.0)

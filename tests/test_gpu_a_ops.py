@@ -97,7 +97,7 @@ def test_rerank_sort_bit_exact_with_ties(e32):
     g = torch.Generator().manual_seed(0)
     for K in (1, 5, 50, 100, 200, 777):
         s = torch.randn(64, K, generator=g)
-        s[:, ::3] = s[:, :1]                 # plant ties
+        s[:, ::3] = s[:, :1].clone()         # plant ties
         s[0, :] = 0.0
         s[1, : K // 2] = -0.0
         order = e32.rerank_sort(s.cuda()).cpu()

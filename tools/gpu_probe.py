@@ -36,20 +36,19 @@ def gemm_probe():
         del A, W
 
 
-def stage2_probe(T_per=2048, C=48, L=32, reps=3):
+def stage2_probe(T_per=2048, C=48, L=32, reps=3, configs=((1024, 32), (2048, 48), (4096, 64), (8192, 128)), Q=512):
     syn = cir.synthetic
     sd2 = syn.make_stage2_state_dict(0, 384, "reference")
     m2 = cir.blip_stage2.blip_stage2(image_size=384, state_dict=sd2, precision="bf16")
     G = 256
     tokens = torch.randn(G, 577, 768, device="cuda").bfloat16()
-    Q = 512
     K = 50
     ids, mask = syn.make_token_ids(Q, L, seed=2)
     ids[:, 0] = 30523
     z_t = torch.randn(Q, L, 768, device="cuda").bfloat16()
     g = torch.Generator().manual_seed(0)
     cand = torch.stack([torch.randperm(G, generator=g)[:K] for _ in range(Q)]).int().numpy()
-    for (mt, mc) in ((1024, 32), (2048, 48), (4096, 64), (8192, 128)):
+    for (mt, mc) in configs:
         m2.engine.max_triplets, m2.engine.max_candidates = mt, mc
         e.launch_count(reset=True)
         ms = timeit(lambda: m2.score_triplets(z_t, ids, mask, tokens, cand), warm=1, it=reps)
@@ -63,3 +62,5 @@ if __name__ == "__main__":
         gemm_probe()
     if "stage2" in which:
         stage2_probe()
+    if "stage2_profile" in which:      # one short pass for an ncu launch list
+        stage2_probe(reps=1, configs=((2048, 48),), Q=96)
