@@ -78,10 +78,8 @@ class BLIP_NLVR(nn.Module):
         ids, mask = tokenize(self.tokenizer, text, e.device)
         cand = e.to_act(t_image_embeds)
         Bt = cand.shape[0]
-        q = torch.arange(B, dtype=torch.int32, device=e.device).repeat_interleave(Bt)
-        c = torch.arange(Bt, dtype=torch.int32, device=e.device).repeat(B)
-        scores, _ = e.stage2_score_chunk(self._w, cand, torch.arange(Bt, dtype=torch.int32, device=e.device), z, ids, mask, q, c)
-        return scores.view(B, Bt)
+        cand_idx = torch.arange(Bt, dtype=torch.int32).expand(B, Bt).numpy()
+        return e.stage2_score_matrix(self._w, cand, z, ids, mask, cand_idx)
 
     # ---- batched fast path used by validate_stage2 (candidate-major, gallery-resident)
     def score_triplets(self, z_t, ids, mask, gallery_tokens, cand_idx, row_active=None):

@@ -102,6 +102,203 @@ attention_simt_kernel(cir_attn_args p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// attention_mma_kernel: bf16 tensor-core (mma.sync m16n8k16, fp32 accumulate) flash attention with
+// online softmax.  One warp = one 16-row query tile ("unit"); the NWARPS warps of a CTA belong to
+// one run of batches that share the same K/V (candidate-major triplets of one candidate image, or
+// the query tiles of one ViT image), so each 64-key K/V chunk is fetched once per CTA into
+// XOR-swizzled shared memory by a 3-stage cp.async pipeline and read by every warp via ldmatrix.
+// Scores never leave registers (no [L,577] round trip, no K^T / V transpose copies).
+constexpr int FA_KC = 64;                       // keys per chunk
+constexpr int FA_STAGES = 3;
+constexpr int FA_STAGE_BYTES = 2 * FA_KC * 128; // K chunk + V chunk, 128 B per key row (64 bf16)
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32)
+attention_mma_kernel(cir_attn_args p, int mt) {
+  extern __shared__ __align__(128) uint8_t fa_smem[];
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(fa_smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  int batch0, unit0, run_units;
+  if (p.work) {
+    const int4 w = reinterpret_cast<const int4*>(p.work)[blockIdx.x];
+    batch0 = w.x; unit0 = w.y; run_units = w.z;
+  } else {
+    const int cpb = (mt + NWARPS - 1) / NWARPS;
+    batch0 = blockIdx.x / cpb; unit0 = (blockIdx.x % cpb) * NWARPS; run_units = mt;
+  }
+  const int h = blockIdx.y;
+  const int u = unit0 + warp;
+  const bool active = u < run_units;
+  const int b = batch0 + (active ? u / mt : 0);
+  const int mi = active ? u % mt : 0;
+  const int kvb = p.kv_index ? p.kv_index[batch0] : batch0;
+  const bf16* Kg = (const bf16*)p.k + (int64_t)kvb * p.k_bs + h * DH;
+  const bf16* Vg = (const bf16*)p.v + (int64_t)kvb * p.v_bs + h * DH;
+  const int nchunks = (p.Lk + FA_KC - 1) / FA_KC;
+
+  auto load_chunk = [&](int c) {
+    if (c < nchunks) {
+      const uint32_t sbase = smem0 + (uint32_t)(c % FA_STAGES) * FA_STAGE_BYTES;
+      for (int idx = tid; idx < 2 * FA_KC * 8; idx += NWARPS * 32) {
+        const int which = idx >> 9, rem = idx & 511, row = rem >> 3, ch = rem & 7;
+        int key = c * FA_KC + row;
+        key = key < p.Lk ? key : p.Lk - 1;                       // clamp: rows past Lk are masked below
+        const bf16* src = (which ? Vg + (int64_t)key * p.v_rs : Kg + (int64_t)key * p.k_rs) + ch * 8;
+        cp_async16(sbase + (uint32_t)which * (FA_KC * 128) + (uint32_t)row * 128 + (uint32_t)((ch ^ (row & 7)) << 4), src);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int c = 0; c < FA_STAGES - 1; c++) load_chunk(c);
+
+  // Q fragments (A operand, 16 rows x 64) straight from global memory
+  const int r0 = mi * 16 + g, r1 = r0 + 8;
+  const bool v0 = active && r0 < p.Lq, v1 = active && r1 < p.Lq;
+  uint32_t qa[4][4];
+  {
+    const bf16* Qb = (const bf16*)p.q + (int64_t)b * p.q_bs + h * DH;
+    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(Qb + (int64_t)r0 * p.q_rs);
+    const uint32_t* q1 = reinterpret_cast<const uint32_t*>(Qb + (int64_t)r1 * p.q_rs);
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      qa[kk][0] = v0 ? q0[kk * 8 + t] : 0u;
+      qa[kk][1] = v1 ? q1[kk * 8 + t] : 0u;
+      qa[kk][2] = v0 ? q0[kk * 8 + 4 + t] : 0u;
+      qa[kk][3] = v1 ? q1[kk * 8 + 4 + t] : 0u;
+    }
+  }
+  const int32_t* mask = (p.key_mask && active) ? p.key_mask + (int64_t)(p.mask_index ? p.mask_index[b] : b) * p.Lk : nullptr;
+  const float sl2 = p.scale * 1.4426950408889634f;          // scores in the log2 domain
+  const float mask_l2 = -10000.0f * 1.4426950408889634f;    // additive -10000 (src/nlvr_encoder.py:774)
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int c = 0; c < nchunks; c++) {
+    cp_async_wait<FA_STAGES - 2>();
+    __syncthreads();                      // chunk c landed for everyone; chunk c-1's stage is free
+    load_chunk(c + FA_STAGES - 1);
+    if (!active) continue;
+    const uint32_t sK = smem0 + (uint32_t)(c % FA_STAGES) * FA_STAGE_BYTES;
+    const uint32_t sV = sK + FA_KC * 128;
+    // ---- S = Q K^T for 64 keys: 8 n-tiles x 4 k-steps
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      const int krow = j * 8 + (lane & 7);
+      const uint32_t rowaddr = sK + (uint32_t)krow * 128;
+      uint32_t kb[4];
+      ldmatrix_x4(rowaddr + (uint32_t)((((lane >> 3)) ^ (krow & 7)) << 4), kb);          // dh chunks 0..3
+      mma_bf16_16816(s[j], qa[0], kb[0], kb[1]);
+      mma_bf16_16816(s[j], qa[1], kb[2], kb[3]);
+      ldmatrix_x4(rowaddr + (uint32_t)(((4 + (lane >> 3)) ^ (krow & 7)) << 4), kb);      // dh chunks 4..7
+      mma_bf16_16816(s[j], qa[2], kb[0], kb[1]);
+      mma_bf16_16816(s[j], qa[3], kb[2], kb[3]);
+    }
+    // ---- scale, mask, online softmax (rows r0 and r1; a row lives in the 4 lanes of a quad)
+    float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int key = c * FA_KC + j * 8 + 2 * t + e;
+        float add = 0.f;
+        if (key >= p.Lk) add = -INFINITY;
+        else if (mask && mask[key] == 0) add = mask_l2;
+        s[j][e] = fmaf(s[j][e], sl2, add);
+        s[j][2 + e] = fmaf(s[j][2 + e], sl2, add);
+        cm0 = fmaxf(cm0, s[j][e]);
+        cm1 = fmaxf(cm1, s[j][2 + e]);
+      }
+    }
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+    const float nm0 = fmaxf(m0, cm0), nm1 = fmaxf(m1, cm1);
+    const float a0 = exp2f(m0 - nm0), a1 = exp2f(m1 - nm1);      // first chunk: exp2(-inf) = 0
+    m0 = nm0; m1 = nm1;
+    l0 *= a0; l1 *= a1;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1; }
+    uint32_t pa[4][4];                    // P as bf16 A fragments: k-step kk covers keys 16kk..16kk+15
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float p00 = exp2f(s[j][0] - m0), p01 = exp2f(s[j][1] - m0);
+      const float p10 = exp2f(s[j][2] - m1), p11 = exp2f(s[j][3] - m1);
+      l0 += p00 + p01; l1 += p10 + p11;
+      pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p00, p01);
+      pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p10, p11);
+    }
+    // ---- O += P V : 4 k-steps (16 keys) x 8 n-tiles (8 dh), V fragments via ldmatrix.trans
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      const int vrow = kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+      const uint32_t rowaddr = sV + (uint32_t)vrow * 128;
+#pragma unroll
+      for (int jp = 0; jp < 4; jp++) {
+        uint32_t vb[4];
+        ldmatrix_x4_trans(rowaddr + (uint32_t)(((2 * jp + (lane >> 4)) ^ (vrow & 7)) << 4), vb);
+        mma_bf16_16816(o[2 * jp], pa[kk], vb[0], vb[1]);
+        mma_bf16_16816(o[2 * jp + 1], pa[kk], vb[2], vb[3]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (!active) return;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  bf16* Ob = (bf16*)p.o + (int64_t)b * p.o_bs + h * DH;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (v0) *reinterpret_cast<uint32_t*>(Ob + (int64_t)r0 * p.o_rs + j * 8 + 2 * t) = pack_bf16(o[j][0] * i0, o[j][1] * i0);
+    if (v1) *reinterpret_cast<uint32_t*>(Ob + (int64_t)r1 * p.o_rs + j * 8 + 2 * t) = pack_bf16(o[j][2] * i1, o[j][3] * i1);
+  }
+}
+
+template <int NWARPS>
+int launch_mma(cir_ctx* ctx, const cir_attn_args* a, int mt) {
+  const int cpb = (mt + NWARPS - 1) / NWARPS;
+  const unsigned gx = a->work ? (unsigned)a->num_work : (unsigned)(a->B * cpb);
+  const size_t smem = FA_STAGES * FA_STAGE_BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CIR_CUDA(cudaFuncSetAttribute(attention_mma_kernel<NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  attention_mma_kernel<NWARPS><<<dim3(gx, (unsigned)a->H), NWARPS * 32, smem, ctx->stream>>>(*a, mt);
+  CIR_LAUNCH_CHECK(ctx);
+  return CIR_OK;
+}
+
 size_t simt_smem_bytes(int Lk) {
   const int lk_pad = (Lk + 3) & ~3;
   return sizeof(float) * (size_t)(QT * DH + KC * (DH + 1) + QT * (lk_pad + 1));
@@ -113,6 +310,18 @@ extern "C" int cir_attention(cir_ctx* ctx, const cir_attn_args* a) {
   if (a->B == 0 || a->Lq == 0) return CIR_OK;
   CIR_CHECK_ARG(a->Lk >= 1 && a->Lk <= 1024, "attention: Lk=%d out of range [1,1024]", a->Lk);
   CIR_CHECK_ARG(a->H >= 1 && a->H <= 65535, "attention: bad head count %d", a->H);
+  if (ctx->dtype == CIR_DTYPE_BF16 && ctx->attn_impl != 1) {
+    // tensor-core path: needs 4-byte aligned rows for the packed loads/stores and 16 B aligned K/V rows
+    CIR_CHECK_ARG((a->q_rs % 2) == 0 && (a->o_rs % 2) == 0 && (a->q_bs % 2) == 0 && (a->o_bs % 2) == 0 &&
+                  (a->k_rs % 8) == 0 && (a->v_rs % 8) == 0 && (a->k_bs % 8) == 0 && (a->v_bs % 8) == 0 &&
+                  ((uintptr_t)a->k & 15) == 0 && ((uintptr_t)a->v & 15) == 0 && ((uintptr_t)a->q & 3) == 0 && ((uintptr_t)a->o & 3) == 0,
+                  "attention: operand strides/alignment not supported by the tensor-core kernel");
+    const int mt = (a->Lq + 15) / 16;
+    if (a->work) { CIR_CHECK_ARG(a->num_work > 0, "attention: empty work list"); return launch_mma<8>(ctx, a, mt); }
+    if (mt <= 2) return launch_mma<2>(ctx, a, mt);
+    if (mt <= 4) return launch_mma<4>(ctx, a, mt);
+    return launch_mma<8>(ctx, a, mt);
+  }
   const size_t smem = simt_smem_bytes(a->Lk);
   dim3 grid((unsigned)a->B, (unsigned)a->H, (unsigned)((a->Lq + QT - 1) / QT));
   if (ctx->dtype == CIR_DTYPE_F32) {

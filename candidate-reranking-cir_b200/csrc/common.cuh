@@ -16,6 +16,7 @@ struct cir_ctx {
   int device;
   int dtype;            // CIR_DTYPE_*
   int gemm_impl;        // CIR_GEMM_*
+  int attn_impl;        // 0 = auto (tensor cores in bf16 mode), 1 = force the CUDA-core kernel
   cudaStream_t stream;
   int num_sms;
   int64_t launches;

@@ -40,6 +40,7 @@ extern "C" int cir_create(cir_ctx** out, int device, int dtype) {
   c->device = device;
   c->dtype = dtype;
   c->gemm_impl = CIR_GEMM_AUTO;
+  c->attn_impl = 0;
   c->stream = 0;
   c->num_sms = prop.multiProcessorCount;
   c->launches = 0;
@@ -53,6 +54,11 @@ extern "C" int cir_set_gemm_impl(cir_ctx* ctx, int impl) {
   CIR_CHECK_ARG(impl >= CIR_GEMM_AUTO && impl <= CIR_GEMM_TCGEN05, "bad gemm impl %d", impl);
   CIR_CHECK_ARG(!(impl == CIR_GEMM_TCGEN05 && ctx->dtype != CIR_DTYPE_BF16), "tcgen05 GEMM needs a bf16 context");
   ctx->gemm_impl = impl;
+  return CIR_OK;
+}
+extern "C" int cir_set_attention_impl(cir_ctx* ctx, int impl) {
+  CIR_CHECK_ARG(impl == 0 || impl == 1, "bad attention impl %d", impl);
+  ctx->attn_impl = impl;
   return CIR_OK;
 }
 extern "C" int cir_get_dtype(const cir_ctx* ctx) { return ctx->dtype; }
@@ -272,6 +278,7 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
                                 const int32_t* cand_list, int64_t C, const void* z_t, const int32_t* ids,
                                 const int32_t* mask, int64_t Q, int64_t L, int64_t N,
                                 const int32_t* trip_query, const int32_t* trip_slot, int64_t T,
+                                const int32_t* attn_work, int64_t num_attn_work,
                                 float* scores, float* feats, void* workspace, size_t workspace_bytes) {
   if (T == 0) return CIR_OK;
   CIR_CHECK_ARG(C >= 1 && Q >= 1, "stage2: need at least one candidate and one query");
@@ -317,6 +324,7 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
       c.o = at(ws.ctxc, s * D, es);
       c.q_bs = L * D; c.q_rs = D; c.k_bs = c.v_bs = N * 4 * D; c.k_rs = c.v_rs = 4 * D; c.o_bs = L * 2 * D; c.o_rs = 2 * D;
       c.kv_index = trip_slot;
+      c.work = attn_work; c.num_work = (int32_t)num_attn_work;
       c.B = (int32_t)T; c.H = CIR_HEADS; c.Lq = (int32_t)L; c.Lk = (int32_t)N; c.scale = 0.125f;
       CIR_TRY(cir_attention(ctx, &c));
     }

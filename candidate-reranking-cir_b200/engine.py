@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import native as N
-from .schedule import plan_chunks
+from .schedule import build_attn_work, plan_chunks
 
 HIDDEN, FFN, LAYERS, EMBED = 768, 3072, 12, 256
 NEG_FILL = -99999.99          # src/validate_stage2.py:123,258
@@ -47,6 +47,10 @@ class Engine:
 
     def set_gemm_impl(self, impl: int):
         N.check(self._lib.cir_set_gemm_impl(self.ctx, impl), "cir_set_gemm_impl")
+
+    def set_attention_impl(self, impl: int):
+        """0 = auto (mma.sync tensor cores in bf16 mode), 1 = CUDA-core kernel (cross-check)."""
+        N.check(self._lib.cir_set_attention_impl(self.ctx, impl), "cir_set_attention_impl")
 
     def launch_count(self, reset: bool = False) -> int:
         return int(self._lib.cir_launch_count(self.ctx, 1 if reset else 0))
@@ -257,8 +261,10 @@ class Engine:
                 "cir_stage1_gallery_embed")
         return out
 
-    def stage2_score_chunk(self, w, gallery_tokens, cand_list, z_t, ids, mask, trip_query, trip_slot, want_feats=False):
-        """One C-ABI call: T triplets sharing C candidates -> (scores fp32 [T], feats fp32 [T,1536] | None)."""
+    def stage2_score_chunk(self, w, gallery_tokens, cand_list, z_t, ids, mask, trip_query, trip_slot, want_feats=False,
+                           attn_work=None):
+        """One C-ABI call: T triplets sharing C candidates -> (scores fp32 [T], feats fp32 [T,1536] | None).
+        ``attn_work``: optional int32 [W,4] K/V-sharing work list (schedule.build_attn_work)."""
         cand_list, ids, mask = self._i32(cand_list), self._i32(ids), self._i32(mask)
         trip_query, trip_slot = self._i32(trip_query), self._i32(trip_slot)
         T, Cn, (Q, L), n_tok = trip_query.numel(), cand_list.numel(), ids.shape, gallery_tokens.shape[1]
@@ -268,10 +274,12 @@ class Engine:
         feats = torch.empty(T, 2 * HIDDEN, dtype=torch.float32, device=self.device) if want_feats else None
         need = self._lib.cir_stage2_workspace_bytes(self.ctx, T, Cn, Q, L, n_tok)
         ws = self.workspace(need)
+        aw = None if attn_work is None or len(attn_work) == 0 else self._i32(attn_work)
         self._sync_stream()
         N.check(self._lib.cir_stage2_score(
             self.ctx, C.byref(w), N.ptr(gallery_tokens), N.ptr(cand_list), Cn, N.ptr(z_t), N.ptr(ids), N.ptr(mask),
-            Q, L, n_tok, N.ptr(trip_query), N.ptr(trip_slot), T, N.ptr(scores), N.ptr(feats), N.ptr(ws), ws.numel()),
+            Q, L, n_tok, N.ptr(trip_query), N.ptr(trip_slot), T, N.ptr(aw), 0 if aw is None else aw.shape[0],
+            N.ptr(scores), N.ptr(feats), N.ptr(ws), ws.numel()),
             "cir_stage2_score")
         return scores, feats
 
@@ -287,7 +295,8 @@ class Engine:
         for ch in chunks:
             ql = torch.from_numpy(ch.query_list.astype(np.int64)).to(self.device)
             s, _ = self.stage2_score_chunk(w, gallery_tokens, ch.cand_list, z_t.index_select(0, ql).contiguous(),
-                                           ids_d.index_select(0, ql), mask_d.index_select(0, ql), ch.trip_query, ch.trip_slot)
+                                           ids_d.index_select(0, ql), mask_d.index_select(0, ql), ch.trip_query, ch.trip_slot,
+                                           attn_work=build_attn_work(ch.trip_slot, ids_d.shape[1]))
             out.index_copy_(0, torch.from_numpy(ch.flat_pos).to(self.device), s)
         return out.view(Q, K)
 
@@ -378,7 +387,7 @@ class Engine:
         N.check(self._lib.cir_gemm(self.ctx, C.byref(g)), "cir_gemm")
         return Cm if batched else Cm[0]
 
-    def attention(self, q, k, v, key_mask=None, kv_index=None, scale=0.125):
+    def attention(self, q, k, v, key_mask=None, kv_index=None, scale=0.125, work=None):
         """q [B,Lq,H*64], k/v [Bk,Lk,H*64] act dtype -> o [B,Lq,H*64]; test hook over cir_attention."""
         B, Lq, HD = q.shape
         Lk = k.shape[1]
@@ -391,6 +400,8 @@ class Engine:
         km = None if key_mask is None else self._i32(key_mask)
         ki = None if kv_index is None else self._i32(kv_index)
         a.key_mask, a.kv_index, a.mask_index = N.ptr(km), N.ptr(ki), N.vp(0)
+        wk = None if work is None else self._i32(work)
+        a.work, a.num_work = N.ptr(wk), (0 if wk is None else wk.shape[0])
         a.B, a.H, a.Lq, a.Lk, a.scale = B, HD // 64, Lq, Lk, scale
         self._sync_stream()
         N.check(self._lib.cir_attention(self.ctx, C.byref(a)), "cir_attention")

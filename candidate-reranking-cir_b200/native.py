@@ -38,7 +38,7 @@ class AttnArgs(C.Structure):
     _fields_ = [("q", vp), ("k", vp), ("v", vp), ("o", vp),
                 ("q_bs", i64), ("q_rs", i64), ("k_bs", i64), ("k_rs", i64),
                 ("v_bs", i64), ("v_rs", i64), ("o_bs", i64), ("o_rs", i64),
-                ("kv_index", vp), ("key_mask", vp), ("mask_index", vp),
+                ("kv_index", vp), ("key_mask", vp), ("mask_index", vp), ("work", vp), ("num_work", i32),
                 ("B", i32), ("H", i32), ("Lq", i32), ("Lk", i32), ("scale", C.c_float)]
 
 
@@ -79,6 +79,7 @@ _SIGS = {
     "cir_destroy": (C.c_int, [vp]),
     "cir_set_stream": (C.c_int, [vp, vp]),
     "cir_set_gemm_impl": (C.c_int, [vp, C.c_int]),
+    "cir_set_attention_impl": (C.c_int, [vp, C.c_int]),
     "cir_get_dtype": (C.c_int, [vp]),
     "cir_launch_count": (i64, [vp, C.c_int]),
     "cir_gemm": (C.c_int, [vp, C.POINTER(GemmArgs)]),
@@ -102,7 +103,7 @@ _SIGS = {
     "cir_stage1_encode": (C.c_int, [vp, C.POINTER(Stage1Weights), vp, vp, vp, vp, i64, i64, i64, vp, vp, C.c_int, vp, C.c_size_t]),
     "cir_stage1_gallery_embed": (C.c_int, [vp, C.POINTER(Stage1Weights), vp, i64, i64, vp, vp, C.c_size_t]),
     "cir_stage2_workspace_bytes": (C.c_size_t, [vp, i64, i64, i64, i64, i64]),
-    "cir_stage2_score": (C.c_int, [vp, C.POINTER(Stage2Weights), vp, vp, i64, vp, vp, vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, C.c_size_t]),
+    "cir_stage2_score": (C.c_int, [vp, C.POINTER(Stage2Weights), vp, vp, i64, vp, vp, vp, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, vp, C.c_size_t]),
 }
 
 _lib = None

@@ -83,6 +83,30 @@ def _make_chunk(flat_pos: np.ndarray, cands: np.ndarray, K: int) -> Chunk:
                  trip_query=trip_query.astype(np.int32))
 
 
+def build_attn_work(trip_slot: np.ndarray, L: int, warps: int = 8) -> np.ndarray:
+    """Cross-attention work list for ``cir_attn_args.work`` (include/cir_b200.h): one CTA of ``warps``
+    16-row query tiles per entry, every entry inside one run of triplets that share a candidate.
+    ``trip_slot`` must be sorted (candidate-major).  Returns int32 [W,4] = (first triplet of the run,
+    first unit, units in the run, 0)."""
+    trip_slot = np.asarray(trip_slot)
+    if trip_slot.size == 0:
+        return np.zeros((0, 4), np.int32)
+    assert np.all(np.diff(trip_slot) >= 0), "trip_slot must be candidate-major (sorted)"
+    mt = (L + 15) // 16
+    starts = np.flatnonzero(np.r_[True, trip_slot[1:] != trip_slot[:-1]])
+    counts = np.diff(np.r_[starts, trip_slot.size])
+    units = counts * mt
+    nctas = (units + warps - 1) // warps
+    run_of = np.repeat(np.arange(starts.size), nctas)
+    first = np.cumsum(nctas) - nctas
+    unit0 = (np.arange(run_of.size) - first[run_of]) * warps
+    out = np.zeros((run_of.size, 4), np.int32)
+    out[:, 0] = starts[run_of]
+    out[:, 1] = unit0
+    out[:, 2] = units[run_of]
+    return out
+
+
 def shard_rows(num_rows: int, rank: int, world: int) -> slice:
     """Contiguous block partition of ``num_rows`` units over ``world`` ranks (first ranks get the
     remainder).  Used for queries (stage II) and gallery rows (stage I)."""

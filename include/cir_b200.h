@@ -64,6 +64,7 @@ int  cir_create(cir_ctx** out, int device, int dtype);
 int  cir_destroy(cir_ctx* ctx);
 int  cir_set_stream(cir_ctx* ctx, void* cuda_stream);       /* cudaStream_t */
 int  cir_set_gemm_impl(cir_ctx* ctx, int impl);              /* CIR_GEMM_* */
+int  cir_set_attention_impl(cir_ctx* ctx, int impl);      /* 0 auto (mma tensor cores in bf16), 1 CUDA-core kernel */
 int  cir_get_dtype(const cir_ctx* ctx);
 /* number of kernel launches issued through this context since the last reset (bench.py's gpu_launches) */
 int64_t cir_launch_count(cir_ctx* ctx, int reset);
@@ -107,6 +108,11 @@ typedef struct cir_attn_args {
   int64_t q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs;
   const int32_t* kv_index; const int32_t* key_mask;
   const int32_t* mask_index;   /* optional int32[B] -> row of key_mask used for batch b (default b) */
+  /* optional K/V-sharing work list, int32 [num_work][4] = {first batch, first 16-row unit, units in
+   * the run, 0}: one CTA per entry; all batches of a run MUST name the same K/V batch (candidate-
+   * major triplets).  A unit is (batch, 16-row query tile): unit u -> batch first+u/mt, tile u%mt,
+   * mt = ceil(Lq/16).  NULL: every batch is its own run. */
+  const int32_t* work; int32_t num_work;
   int32_t B, H, Lq, Lk;
   float scale;
 } cir_attn_args;
@@ -241,12 +247,15 @@ typedef struct cir_stage2_weights {
  *   gallery_tokens act [G,N,768]; cand_list int32 [C] gallery rows of the chunk's candidates
  *   z_t act [Q,L,768]; ids/mask int32 [Q,L]
  *   trip_query int32 [T] -> row of z_t/ids/mask; trip_slot int32 [T] -> position in cand_list
+ *   attn_work int32 [W,4] optional cross-attention work list (see cir_attn_args.work; requires trip_slot
+ *   sorted so that triplets naming the same candidate are adjacent)
  *   scores fp32 [T] (class-0 logit); feats fp32 [T,1536] optional (cat(CLS0,CLS1), nlvr_encoder.py:909) */
 size_t cir_stage2_workspace_bytes(const cir_ctx* ctx, int64_t T, int64_t C, int64_t Q, int64_t L, int64_t N);
 int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const void* gallery_tokens,
                      const int32_t* cand_list, int64_t C, const void* z_t, const int32_t* ids,
                      const int32_t* mask, int64_t Q, int64_t L, int64_t N,
                      const int32_t* trip_query, const int32_t* trip_slot, int64_t T,
+                     const int32_t* attn_work, int64_t num_attn_work,
                      float* scores, float* feats, void* workspace, size_t workspace_bytes);
 
 #ifdef __cplusplus

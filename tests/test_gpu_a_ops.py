@@ -179,3 +179,31 @@ def test_embeddings_and_normalize(e32):
     y = torch.empty_like(x)
     N_.check(e32._lib.cir_l2_normalize(e32.ctx, N_.ptr(x), N_.ptr(y), 11, 256))
     assert (y - torch.nn.functional.normalize(x, dim=-1)).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("B,Lq,Lk,masked", [(5, 32, 577, False), (7, 12, 577, False), (3, 40, 577, False), (6, 32, 32, True),
+                                            (4, 12, 12, True), (2, 577, 577, False), (9, 32, 100, True)])
+def test_attention_mma_vs_reference(e16, B, Lq, Lk, masked):
+    q = _rand(B, Lq, 768, seed=1).bfloat16()
+    nkv = 3
+    k = _rand(nkv, Lk, 768, seed=2).bfloat16()
+    v = _rand(nkv, Lk, 768, seed=3).bfloat16()
+    kv_index = torch.tensor(sorted(i % nkv for i in range(B)), dtype=torch.int32).cuda()
+    mask = None
+    if masked:
+        mask = torch.ones(B, Lk, dtype=torch.int32)
+        for b in range(B):
+            mask[b, Lk - 1 - (b % 5):] = 0
+        mask = mask.cuda()
+    ref = ref_attention(q, k, v, mask, kv_index)
+    o = e16.attention(q, k, v, key_mask=mask, kv_index=kv_index)              # tensor cores, one run per batch
+    assert (o.float() - ref).abs().max() < 2.5e-2
+    work = cir.schedule.build_attn_work(kv_index.cpu().numpy(), Lq)            # K/V shared inside candidate runs
+    o2 = e16.attention(q, k, v, key_mask=mask, kv_index=kv_index, work=work)
+    assert (o2.float() - ref).abs().max() < 2.5e-2
+    e16.set_attention_impl(1)
+    try:
+        o3 = e16.attention(q, k, v, key_mask=mask, kv_index=kv_index)          # CUDA-core kernel on the same inputs
+    finally:
+        e16.set_attention_impl(0)
+    assert (o.float() - o3.float()).abs().max() < 2.5e-2

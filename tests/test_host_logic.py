@@ -99,3 +99,21 @@ def test_random_topk_plants_targets():
     assert not (cand.long() == ref[:, None]).any()
     assert all(len(set(r.tolist())) == 10 for r in cand)
     assert 0.7 < labels.any(1).float().mean() <= 1.0
+
+
+def test_build_attn_work_units():
+    from importlib import import_module
+    sched = import_module("candidate-reranking-cir_b200.schedule")
+    slot = np.array([0, 0, 0, 0, 0, 1, 3, 3], np.int32)
+    for L, warps in ((32, 8), (12, 8), (40, 8), (32, 2)):
+        mt = (L + 15) // 16
+        w = sched.build_attn_work(slot, L, warps)
+        covered = set()
+        for b0, u0, nu, _ in w.tolist():
+            for u in range(u0, min(u0 + warps, nu)):
+                t, mi = b0 + u // mt, u % mt
+                assert slot[t] == slot[b0]
+                assert (t, mi) not in covered
+                covered.add((t, mi))
+        assert covered == {(t, mi) for t in range(len(slot)) for mi in range(mt)}
+    assert sched.build_attn_work(np.zeros(0, np.int32), 32).shape == (0, 4)
