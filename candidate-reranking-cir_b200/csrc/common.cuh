@@ -21,7 +21,12 @@ struct cir_ctx {
   int num_sms;
   int64_t launches;
   void* encode_tiled;   // cuTensorMapEncodeTiled entry point (PFN), resolved lazily
+  // optional per-launch GEMM timing (bench.py roofline): event pairs around every tcgen05 GEMM launch
+  int profiling;
+  void* prof;           // ProfState*
 };
+void cir_prof_gemm_begin(cir_ctx* ctx, double flops);
+void cir_prof_gemm_end(cir_ctx* ctx);
 
 void cir_set_error(const char* fmt, ...);
 

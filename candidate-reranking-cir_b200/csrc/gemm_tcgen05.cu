@@ -30,7 +30,7 @@ template <int BN> struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;            // 32 / 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = ACC_STAGES * BN;      // 512 / 256
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 192 /*barriers*/ + ACC_STAGES * BN * 4 /*bias*/;
 };
 
 struct Params {
@@ -252,10 +252,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else {
     // ===================== epilogue (8 warps) =====================
+    // Latency matters more than bandwidth here (8 warps, dependent chains), so: the tile's bias row is
+    // staged in shared memory BEFORE the accumulator is waited for, bf16 residual rows are prefetched
+    // into registers ahead of the TMEM load, and two 32-column chunks are in flight per tcgen05.wait.
     const int ew = warp - 2;                 // 0..7
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access (warp_id % 4)
     const int half = ew >> 2;                // which half of the BN columns
     constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int NCH = COLS_PER_WARP / 32;  // 4 or 2 (even)
+    float* sbias = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES + 192);   // [ACC_STAGES][BN]
+    const int etid = threadIdx.x - 64;       // 0..255
+    const bool res_bf16_fast = p.residual && !p.res_f32 && (p.ldres & 7) == 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_batch;
@@ -263,33 +270,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int m_blk = r / p.n_blocks, n_blk = r - m_blk * p.n_blocks;
       const int64_t row = (int64_t)m_blk * BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
+      const int64_t ntile0 = (int64_t)n_blk * BN;
+      if (etid < BN) {
+        const int64_t n = ntile0 + etid;
+        sbias[acc * BN + etid] = (p.bias && n < p.N) ? __ldg(p.bias + b * p.bias_bstride + n) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // epilogue warps only
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      const float* bias = p.bias ? p.bias + b * p.bias_bstride : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP / 32; c++) {
+
+      auto finish = [&](int c, uint32_t (&v)[32], const uint4 (&rq)[4], bool have_rq) {
         const int col0 = half * COLS_PER_WARP + c * 32;
-        const int64_t n0 = (int64_t)n_blk * BN + col0;
-        uint32_t v[32];
-        __syncwarp();                                 // tcgen05.ld is .sync.aligned: reconverge first
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col0), v);
-        tmem_ld_wait();
-        if (n0 >= p.N || !row_ok) continue;           // N tail chunk / M tail row: nothing to store
+        const int64_t n0 = ntile0 + col0;
+        if (n0 >= p.N || !row_ok) return;              // N tail chunk / M tail row: nothing to store
         const bool full = (n0 + 32 <= p.N);
         float f[32];
+        const float4* sb = reinterpret_cast<const float4*>(sbias + acc * BN + col0);
 #pragma unroll
-        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
-        if (bias) {
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + j));
-              f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j++) if (n0 + j < p.N) f[j] += __ldg(bias + n0 + j);
-          }
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bv = sb[j >> 2];
+          f[j] = __uint_as_float(v[j]) + bv.x; f[j + 1] = __uint_as_float(v[j + 1]) + bv.y;
+          f[j + 2] = __uint_as_float(v[j + 2]) + bv.z; f[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
         }
         if (p.act == CIR_ACT_GELU) {
 #pragma unroll
@@ -300,12 +301,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         if (p.residual) {
           const int64_t ro = b * p.res_bstride + row * p.ldres + n0;
-          if (p.res_f32) {
+          if (have_rq) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rq[j]);
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const float2 t = __bfloat1622float2(h2[q]);
+                f[j * 8 + 2 * q] += t.x; f[j * 8 + 2 * q + 1] += t.y;
+              }
+            }
+          } else if (p.res_f32) {
             const float* rp = (const float*)p.residual + ro;
             if (full && (p.ldres & 3) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                float4 rv = *reinterpret_cast<const float4*>(rp + j);
+                const float4 rv = *reinterpret_cast<const float4*>(rp + j);
                 f[j] += rv.x; f[j + 1] += rv.y; f[j + 2] += rv.z; f[j + 3] += rv.w;
               }
             } else {
@@ -314,21 +325,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
           } else {
             const bf16* rp = (const bf16*)p.residual + ro;
-            if (full && (p.ldres & 7) == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 rv = *reinterpret_cast<const uint4*>(rp + j);
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                  float2 t = __bfloat1622float2(h2[q]);
-                  f[j + 2 * q] += t.x; f[j + 2 * q + 1] += t.y;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j++) if (n0 + j < p.N) f[j] += __bfloat162float(rp[j]);
-            }
+            for (int j = 0; j < 32; j++) if (n0 + j < p.N) f[j] += __bfloat162float(rp[j]);
           }
         }
         const int64_t co = b * p.c_bstride + row * p.ldc + n0;
@@ -357,6 +355,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int j = 0; j < 32; j++) if (n0 + j < p.N) cp[j] = __float2bfloat16_rn(f[j]);
           }
         }
+      };
+
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        uint4 rq0[4], rq1[4];
+        bool have0 = false, have1 = false;
+        if (res_bf16_fast && row_ok) {                 // residual rows do not depend on the accumulator: fetch first
+          const int64_t n00 = ntile0 + half * COLS_PER_WARP + c * 32;
+          const bf16* rp = (const bf16*)p.residual + b * p.res_bstride + row * p.ldres + n00;
+          have0 = n00 + 32 <= p.N;
+          have1 = n00 + 64 <= p.N;
+          if (have0) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) rq0[j] = *reinterpret_cast<const uint4*>(rp + j * 8);
+          }
+          if (have1) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) rq1[j] = *reinterpret_cast<const uint4*>(rp + 32 + j * 8);
+          }
+        }
+        uint32_t v0[32], v1[32];
+        __syncwarp();                                  // tcgen05.ld is .sync.aligned: reconverge first
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * COLS_PER_WARP + c * 32);
+        tmem_ld_32x32b_x32(taddr, v0);
+        tmem_ld_32x32b_x32(taddr + 32, v1);
+        tmem_ld_wait();
+        finish(c, v0, rq0, have0);
+        finish(c + 1, v1, rq1, have1);
       }
       // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator back
       tcgen05_fence_before();
@@ -424,7 +450,9 @@ static int launch_tc(cir_ctx* ctx, const cir_gemm_args* a, const tc::Params& p, 
     attr_set = true;
   }
   int grid = p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms;
+  cir_prof_gemm_begin(ctx, 2.0 * (double)p.M * (double)p.N * (double)p.K * (double)p.batch);
   tc::gemm_tcgen05_kernel<BN><<<grid, tc::THREADS, C::SMEM_BYTES, ctx->stream>>>(ma, mw, p);
+  cir_prof_gemm_end(ctx);
   CIR_LAUNCH_CHECK(ctx);
   (void)a;
   return CIR_OK;

@@ -12,6 +12,31 @@ int cir_vit_assemble(cir_ctx* ctx, const float* patch, const float* cls, const f
 int cir_gather_cls(cir_ctx* ctx, const void* h, int64_t T, int64_t L, void* feats, float* feats_f32);
 int cir_head_dot(cir_ctx* ctx, const float* hidden, const float* w, const float* b, float* scores, int64_t rows);
 
+#include <vector>
+struct ProfState {
+  std::vector<cudaEvent_t> ev;      // pairs: [2i] start, [2i+1] end
+  std::vector<double> flops;
+  size_t used = 0;                  // pairs in use
+};
+void cir_prof_gemm_begin(cir_ctx* ctx, double flops) {
+  if (!ctx->profiling) return;
+  ProfState* ps = (ProfState*)ctx->prof;
+  if (ps->used * 2 + 2 > ps->ev.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    ps->ev.push_back(a); ps->ev.push_back(b);
+    ps->flops.push_back(0.0);
+  }
+  ps->flops[ps->used] = flops;
+  cudaEventRecord(ps->ev[ps->used * 2], ctx->stream);
+}
+void cir_prof_gemm_end(cir_ctx* ctx) {
+  if (!ctx->profiling) return;
+  ProfState* ps = (ProfState*)ctx->prof;
+  cudaEventRecord(ps->ev[ps->used * 2 + 1], ctx->stream);
+  ps->used++;
+}
+
 static thread_local char g_err[1024] = "";
 void cir_set_error(const char* fmt, ...) {
   va_list ap;
@@ -45,10 +70,37 @@ extern "C" int cir_create(cir_ctx** out, int device, int dtype) {
   c->num_sms = prop.multiProcessorCount;
   c->launches = 0;
   c->encode_tiled = nullptr;
+  c->profiling = 0;
+  c->prof = new ProfState();
   *out = c;
   return CIR_OK;
 }
-extern "C" int cir_destroy(cir_ctx* ctx) { delete ctx; return CIR_OK; }
+extern "C" int cir_destroy(cir_ctx* ctx) {
+  if (!ctx) return CIR_OK;
+  ProfState* ps = (ProfState*)ctx->prof;
+  for (cudaEvent_t e : ps->ev) cudaEventDestroy(e);
+  delete ps;
+  delete ctx;
+  return CIR_OK;
+}
+extern "C" int cir_profile_gemm(cir_ctx* ctx, int enable) {
+  ProfState* ps = (ProfState*)ctx->prof;
+  ctx->profiling = enable ? 1 : 0;
+  if (enable) ps->used = 0;
+  return CIR_OK;
+}
+extern "C" int cir_profile_gemm_read(cir_ctx* ctx, double* total_ms, double* total_flops, int64_t* launches) {
+  ProfState* ps = (ProfState*)ctx->prof;
+  double ms = 0.0, fl = 0.0;
+  for (size_t i = 0; i < ps->used; i++) {
+    float t = 0.f;
+    CIR_CUDA(cudaEventSynchronize(ps->ev[2 * i + 1]));
+    CIR_CUDA(cudaEventElapsedTime(&t, ps->ev[2 * i], ps->ev[2 * i + 1]));
+    ms += t; fl += ps->flops[i];
+  }
+  *total_ms = ms; *total_flops = fl; *launches = (int64_t)ps->used;
+  return CIR_OK;
+}
 extern "C" int cir_set_stream(cir_ctx* ctx, void* s) { ctx->stream = (cudaStream_t)s; return CIR_OK; }
 extern "C" int cir_set_gemm_impl(cir_ctx* ctx, int impl) {
   CIR_CHECK_ARG(impl >= CIR_GEMM_AUTO && impl <= CIR_GEMM_TCGEN05, "bad gemm impl %d", impl);

@@ -52,6 +52,15 @@ class Engine:
         """0 = auto (mma.sync tensor cores in bf16 mode), 1 = CUDA-core kernel (cross-check)."""
         N.check(self._lib.cir_set_attention_impl(self.ctx, impl), "cir_set_attention_impl")
 
+    def profile_gemm(self, enable: bool):
+        N.check(self._lib.cir_profile_gemm(self.ctx, 1 if enable else 0))
+
+    def profile_gemm_read(self):
+        """-> (summed GEMM ms, summed algorithmic FLOPs, launches) since profile_gemm(True)."""
+        ms, fl, n = C.c_double(), C.c_double(), N.i64()
+        N.check(self._lib.cir_profile_gemm_read(self.ctx, C.byref(ms), C.byref(fl), C.byref(n)))
+        return ms.value, fl.value, n.value
+
     def launch_count(self, reset: bool = False) -> int:
         return int(self._lib.cir_launch_count(self.ctx, 1 if reset else 0))
 

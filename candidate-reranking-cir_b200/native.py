@@ -82,6 +82,8 @@ _SIGS = {
     "cir_set_attention_impl": (C.c_int, [vp, C.c_int]),
     "cir_get_dtype": (C.c_int, [vp]),
     "cir_launch_count": (i64, [vp, C.c_int]),
+    "cir_profile_gemm": (C.c_int, [vp, C.c_int]),
+    "cir_profile_gemm_read": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]),
     "cir_gemm": (C.c_int, [vp, C.POINTER(GemmArgs)]),
     "cir_add_layernorm": (C.c_int, [vp, vp, C.c_int, i64, vp, vp, vp, i64, vp, C.c_int, i64, C.c_float]),
     "cir_attention": (C.c_int, [vp, C.POINTER(AttnArgs)]),

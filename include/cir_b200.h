@@ -69,6 +69,12 @@ int  cir_get_dtype(const cir_ctx* ctx);
 /* number of kernel launches issued through this context since the last reset (bench.py's gpu_launches) */
 int64_t cir_launch_count(cir_ctx* ctx, int reset);
 
+/* per-launch timing of the tcgen05 GEMM (CUDA events on the context's stream around every GEMM launch);
+ * cir_profile_gemm(ctx,1) resets and starts, (ctx,0) stops; _read synchronises on the recorded events and
+ * returns summed duration, summed algorithmic FLOPs (2*M*N*K*batch) and the launch count. */
+int  cir_profile_gemm(cir_ctx* ctx, int enable);
+int  cir_profile_gemm_read(cir_ctx* ctx, double* total_ms, double* total_flops, int64_t* launches);
+
 /* ---- primitive ops (each replaces one ATen call of the reference; used by the pipelines
  *      below and individually by the parity tests) ------------------------------------- */
 

@@ -1,0 +1,25 @@
+"""Key metrics of every kernel in an `ncu --set full` report (run here, no GPU needed):
+   python tools/ncu_summary.py gpurun_out/x.ncu-rep"""
+import csv, subprocess, sys
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.max", "launch__shared_mem_per_block_dynamic"]
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        print(f"== {r[idx['Kernel Name']][:110]}")
+        for w in WANT:
+            if w in idx:
+                print(f"   {w:72s} {r[idx[w]]:>16s} {units[idx[w]]}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
