@@ -17,6 +17,7 @@ struct cir_ctx {
   int dtype;            // CIR_DTYPE_*
   int gemm_impl;        // CIR_GEMM_*
   int attn_impl;        // 0 = auto (tensor cores in bf16 mode), 1 = force the CUDA-core kernel
+  int gemm_pair;        // 1 = allow cta_group::2 pair tiles for large GEMMs (default)
   cudaStream_t stream;
   int num_sms;
   int64_t launches;

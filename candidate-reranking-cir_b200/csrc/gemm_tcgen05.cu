@@ -24,13 +24,18 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int THREADS = 64 + NUM_EPI_WARPS * 32;   // 320
 constexpr int ACC_STAGES = 2;
 
-template <int BN> struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+// PAIR = cta_group::2: two CTAs of a cluster compute one 256 x BN tile; each CTA stages its own 128 rows
+// of A and HALF of the W tile (the tensor core reads the other half from the peer's shared memory), so
+// L2->SM operand traffic per output drops 1.5x versus the single-CTA 128 x 256 tile.
+template <int BN, bool PAIR = false> struct Cfg {
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;      // W rows staged by this CTA
   static constexpr int A_BYTES = BM * BK * 2;            // 16 KB
-  static constexpr int B_BYTES = BN * BK * 2;            // 32 / 16 KB
+  static constexpr int B_BYTES = B_ROWS * BK * 2;        // 32 / 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_STAGING = NUM_EPI_WARPS * 4096;   // per-warp 32 x 128 B transpose tiles
+  static constexpr int STAGES = (196608 - EPI_STAGING) / STAGE_BYTES;    // 5 (32 KB stages) or 3 (48 KB stages)
   static constexpr int TMEM_COLS = ACC_STAGES * BN;      // 512 / 256
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 192 /*barriers*/ + ACC_STAGES * BN * 4 /*bias*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 192 /*barriers*/ + ACC_STAGES * BN * 4 /*bias*/ + EPI_STAGING;
 };
 
 struct Params {
@@ -108,6 +113,47 @@ template <int COLS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr)
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
 
+template <int COLS> __device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS> __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> even (leader) CTA of the pair
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// both CTAs of the pair issue this; the transaction bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same offset in BOTH CTAs once the pair's MMAs retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -156,22 +202,27 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// Abramowitz-Stegun 7.1.26 erf (|err| < 1.5e-7, far below bf16 resolution): ~12 instructions
-// instead of erff's ~40, so the GELU epilogue keeps up with the MMA pipe.
+// GELU in the bf16 epilogue: the tanh form with the hardware tanh.approx (one MUFU + 6 FMA-pipe ops per
+// element; the erf form costs two MUFU + ~14 ops and made the FFN1 epilogue slower than its MMAs).
+// |gelu_tanh - gelu_erf| <= 5e-4 and tanh.approx adds <= 2^-11 relative, both below the bf16 output
+// rounding (2^-9 relative); the fp32 check mode uses the exact erff GELU (gemm_simt.cu).
 __device__ __forceinline__ float gelu_fast(float x) {
-  float z = fabsf(x) * 0.70710678118654752440f;
-  float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-  float erf_abs = 1.0f - poly * __expf(-z * z);
-  float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);     // sqrt(2/pi) * (x + 0.044715 x^3)
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 // ----------------------------------------------------------------------------- the kernel
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
+  constexpr int TILE_M = PAIR ? 2 * BM : BM;                 // rows of one scheduled tile
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;       // 0 = leader (issues the MMAs)
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
   const uint32_t smem_a = smem_base;
@@ -193,12 +244,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_w);
     for (int s = 0; s < C::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < ACC_STAGES; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), NUM_EPI_WARPS); }
+    for (int s = 0; s < ACC_STAGES; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), NUM_EPI_WARPS * (PAIR ? 2 : 1)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_ptr_smem);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair<C::TMEM_COLS>(tmem_ptr_smem);
+    else tmem_alloc<C::TMEM_COLS>(tmem_ptr_smem);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if constexpr (PAIR) cluster_sync_all();      // the peer's barriers must exist before any remote arrive / multicast commit
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -208,28 +264,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ===================== TMA producer =====================
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < p.num_tiles; tile += num_workers) {
         const int b = tile / tiles_per_batch;
         const int r = tile - b * tiles_per_batch;
         const int m_blk = r / p.n_blocks, n_blk = r - m_blk * p.n_blocks;
-        const int32_t a_row = (int32_t)(b * p.a_rows_per_batch + (int64_t)m_blk * BM);
-        const int32_t w_row = (int32_t)(b * p.w_rows_per_batch + (int64_t)n_blk * BN);
+        const int32_t a_row = (int32_t)(b * p.a_rows_per_batch + (int64_t)m_blk * TILE_M + rank * BM);
+        const int32_t w_row = (int32_t)(b * p.w_rows_per_batch + (int64_t)n_blk * BN + rank * C::B_ROWS);
         for (int kb = 0; kb < p.k_blocks; kb++) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-          tma_load_2d(smem_a + stage * C::A_BYTES, &map_a, full_bar(stage), kb * BK, a_row);
-          tma_load_2d(smem_b + stage * C::B_BYTES, &map_w, full_bar(stage), kb * BK, w_row);
+          mbar_wait(empty_bar(stage), phase ^ 1);           // local: freed by the (multicast) MMA commit
+          if constexpr (PAIR) {
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);     // both CTAs' bytes land on the leader's barrier
+            tma_load_2d_pair(smem_a + stage * C::A_BYTES, &map_a, full_bar(stage), kb * BK, a_row);
+            tma_load_2d_pair(smem_b + stage * C::B_BYTES, &map_w, full_bar(stage), kb * BK, w_row);
+          } else {
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            tma_load_2d(smem_a + stage * C::A_BYTES, &map_a, full_bar(stage), kb * BK, a_row);
+            tma_load_2d(smem_b + stage * C::B_BYTES, &map_w, full_bar(stage), kb * BK, w_row);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < p.num_tiles; tile += num_workers) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);          // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -241,34 +303,54 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; k++) {
             // advance 32 B (16 bf16) along K inside the 128 B swizzle atom: +2 in the >>4 address field
-            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+            if constexpr (PAIR) umma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+            else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
           }
-          umma_commit(empty_bar(stage));                    // frees the smem slot when the MMAs retire
+          if constexpr (PAIR) umma_commit_pair(empty_bar(stage));   // frees the slot in BOTH CTAs when the MMAs retire
+          else umma_commit(empty_bar(stage));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(acc));                        // accumulator ready for the epilogue
+        if constexpr (PAIR) umma_commit_pair(tfull_bar(acc));       // accumulator halves ready in both CTAs
+        else umma_commit(tfull_bar(acc));
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
     // ===================== epilogue (8 warps) =====================
-    // Latency matters more than bandwidth here (8 warps, dependent chains), so: the tile's bias row is
-    // staged in shared memory BEFORE the accumulator is waited for, bf16 residual rows are prefetched
-    // into registers ahead of the TMEM load, and two 32-column chunks are in flight per tcgen05.wait.
+    // Each warp owns 32 accumulator rows (its TMEM lane quarter) x BN/2 columns and walks them in spans of
+    // 64 columns.  tcgen05.ld hands every thread one ROW (32 consecutive columns per load), which is the
+    // worst possible shape for global memory (a warp-wide 16 B store would touch 32 different lines), so
+    // rows are transposed through a warp-private, XOR-swizzled 4 KB shared-memory tile: global stores
+    // (and bf16 residual loads) then move whole 128 B row segments, 4 rows per instruction.  The tile's
+    // bias row is staged in shared memory before the accumulator is waited for, and residual segments
+    // are fetched ahead of the TMEM load.
     const int ew = warp - 2;                 // 0..7
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access (warp_id % 4)
     const int half = ew >> 2;                // which half of the BN columns
     constexpr int COLS_PER_WARP = BN / 2;
     constexpr int NCH = COLS_PER_WARP / 32;  // 4 or 2 (even)
-    float* sbias = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES + 192);   // [ACC_STAGES][BN]
+    float* sbias = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES + 192);                  // [ACC_STAGES][BN]
+    const uint32_t stg = bar_base + 192 + ACC_STAGES * BN * 4 + (uint32_t)ew * 4096;                      // this warp's 32 x 128 B tile
     const int etid = threadIdx.x - 64;       // 0..255
     const bool res_bf16_fast = p.residual && !p.res_f32 && (p.ldres & 7) == 0;
+    const bool out_bf16_fast = !p.c_f32 && (p.ldc & 7) == 0;
+    const bool out_f32_fast = p.c_f32 && (p.ldc & 3) == 0;
+    const int lr = lane >> 3, lp = lane & 7; // coalesced mapping: 4 rows x 8 sixteen-byte pieces per instruction
+    auto sts128 = [](uint32_t addr, const uint4& v) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    };
+    auto lds128 = [](uint32_t addr) {
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+      return v;
+    };
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < p.num_tiles; tile += num_workers) {
       const int b = tile / tiles_per_batch;
       const int r = tile - b * tiles_per_batch;
       const int m_blk = r / p.n_blocks, n_blk = r - m_blk * p.n_blocks;
-      const int64_t row = (int64_t)m_blk * BM + quarter * 32 + lane;
+      const int64_t row_base = (int64_t)m_blk * TILE_M + rank * BM + quarter * 32;
+      const int64_t row = row_base + lane;
       const bool row_ok = row < p.M;
       const int64_t ntile0 = (int64_t)n_blk * BN;
       if (etid < BN) {
@@ -279,124 +361,142 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 
-      auto finish = [&](int c, uint32_t (&v)[32], const uint4 (&rq)[4], bool have_rq) {
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
         const int col0 = half * COLS_PER_WARP + c * 32;
-        const int64_t n0 = ntile0 + col0;
-        if (n0 >= p.N || !row_ok) return;              // N tail chunk / M tail row: nothing to store
-        const bool full = (n0 + 32 <= p.N);
-        float f[32];
-        const float4* sb = reinterpret_cast<const float4*>(sbias + acc * BN + col0);
+        const int64_t n00 = ntile0 + col0;                 // first column of this 64-column span
+        const bool span_full = n00 + 64 <= p.N;
+        // ---- bf16 residual: coalesced fetch now (does not depend on the accumulator), transpose after the TMEM wait
+        const bool res_fast = res_bf16_fast && span_full;
+        uint4 rq[8];
+        if (res_fast) {
+          const bf16* rp = (const bf16*)p.residual + b * p.res_bstride + n00 + lp * 8;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bv = sb[j >> 2];
-          f[j] = __uint_as_float(v[j]) + bv.x; f[j + 1] = __uint_as_float(v[j + 1]) + bv.y;
-          f[j + 2] = __uint_as_float(v[j + 2]) + bv.z; f[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
+          for (int it = 0; it < 8; it++) {
+            const int64_t rg = row_base + it * 4 + lr;
+            rq[it] = rg < p.M ? *reinterpret_cast<const uint4*>(rp + rg * p.ldres) : make_uint4(0, 0, 0, 0);
+          }
+        }
+        uint32_t v0[32], v1[32];
+        __syncwarp();                                      // tcgen05.ld is .sync.aligned: reconverge first
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col0);
+        tmem_ld_32x32b_x32(taddr, v0);
+        tmem_ld_32x32b_x32(taddr + 32, v1);
+        tmem_ld_wait();
+        if (n00 >= p.N) continue;                          // whole span beyond N (warp-uniform)
+        float f[64];
+        {
+          const float4* sb = reinterpret_cast<const float4*>(sbias + acc * BN + col0);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b0 = sb[j >> 2], b1 = sb[8 + (j >> 2)];
+            f[j] = __uint_as_float(v0[j]) + b0.x; f[j + 1] = __uint_as_float(v0[j + 1]) + b0.y;
+            f[j + 2] = __uint_as_float(v0[j + 2]) + b0.z; f[j + 3] = __uint_as_float(v0[j + 3]) + b0.w;
+            f[32 + j] = __uint_as_float(v1[j]) + b1.x; f[32 + j + 1] = __uint_as_float(v1[j + 1]) + b1.y;
+            f[32 + j + 2] = __uint_as_float(v1[j + 2]) + b1.z; f[32 + j + 3] = __uint_as_float(v1[j + 3]) + b1.w;
+          }
         }
         if (p.act == CIR_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) f[j] = gelu_fast(f[j]);
+          for (int j = 0; j < 64; j++) f[j] = gelu_fast(f[j]);
         } else if (p.act == CIR_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) f[j] = fmaxf(f[j], 0.f);
+          for (int j = 0; j < 64; j++) f[j] = fmaxf(f[j], 0.f);
         }
         if (p.residual) {
-          const int64_t ro = b * p.res_bstride + row * p.ldres + n0;
-          if (have_rq) {
+          if (res_fast) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rq[j]);
+            for (int it = 0; it < 8; it++) sts128(stg + (uint32_t)(it * 4 + lr) * 128 + (uint32_t)((lp ^ ((it * 4 + lr) & 7)) << 4), rq[it]);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const uint4 rv = lds128(stg + (uint32_t)lane * 128 + (uint32_t)((j ^ (lane & 7)) << 4));
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
               for (int q = 0; q < 4; q++) {
                 const float2 t = __bfloat1622float2(h2[q]);
                 f[j * 8 + 2 * q] += t.x; f[j * 8 + 2 * q + 1] += t.y;
               }
             }
-          } else if (p.res_f32) {
-            const float* rp = (const float*)p.residual + ro;
-            if (full && (p.ldres & 3) == 0) {
+            __syncwarp();
+          } else if (row_ok) {
+            const int64_t ro = b * p.res_bstride + row * p.ldres + n00;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 rv = *reinterpret_cast<const float4*>(rp + j);
-                f[j] += rv.x; f[j + 1] += rv.y; f[j + 2] += rv.z; f[j + 3] += rv.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j++) if (n0 + j < p.N) f[j] += rp[j];
+            for (int j = 0; j < 64; j++) {
+              if (n00 + j < p.N) f[j] += p.res_f32 ? ((const float*)p.residual)[ro + j] : __bfloat162float(((const bf16*)p.residual)[ro + j]);
             }
-          } else {
-            const bf16* rp = (const bf16*)p.residual + ro;
-#pragma unroll
-            for (int j = 0; j < 32; j++) if (n0 + j < p.N) f[j] += __bfloat162float(rp[j]);
           }
         }
-        const int64_t co = b * p.c_bstride + row * p.ldc + n0;
-        if (p.c_f32) {
-          float* cp = (float*)p.C + co;
-          if (full && (p.ldc & 3) == 0) {
+        // ---- store
+        if (out_bf16_fast && span_full) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
+          for (int j = 0; j < 8; j++) {
+            uint4 ov;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
-            for (int j = 0; j < 32; j++) if (n0 + j < p.N) cp[j] = f[j];
+            for (int q = 0; q < 4; q++) h2[q] = __floats2bfloat162_rn(f[j * 8 + 2 * q], f[j * 8 + 2 * q + 1]);
+            sts128(stg + (uint32_t)lane * 128 + (uint32_t)((j ^ (lane & 7)) << 4), ov);
           }
-        } else {
-          bf16* cp = (bf16*)p.C + co;
-          if (full && (p.ldc & 7) == 0) {
+          __syncwarp();
+          bf16* cp = (bf16*)p.C + b * p.c_bstride + n00 + lp * 8;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 ov;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+          for (int it = 0; it < 8; it++) {
+            const int rr = it * 4 + lr;
+            const uint4 ov = lds128(stg + (uint32_t)rr * 128 + (uint32_t)((lp ^ (rr & 7)) << 4));
+            const int64_t rg = row_base + rr;
+            if (rg < p.M) *reinterpret_cast<uint4*>(cp + rg * p.ldc) = ov;
+          }
+          __syncwarp();
+        } else if (out_f32_fast && span_full) {
 #pragma unroll
-              for (int q = 0; q < 4; q++) h2[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
-              *reinterpret_cast<uint4*>(cp + j) = ov;
+          for (int hh = 0; hh < 2; hh++) {                  // 32 fp32 columns = 128 B per row per pass
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const uint4 ov = make_uint4(__float_as_uint(f[hh * 32 + j * 4]), __float_as_uint(f[hh * 32 + j * 4 + 1]),
+                                          __float_as_uint(f[hh * 32 + j * 4 + 2]), __float_as_uint(f[hh * 32 + j * 4 + 3]));
+              sts128(stg + (uint32_t)lane * 128 + (uint32_t)((j ^ (lane & 7)) << 4), ov);
             }
-          } else {
+            __syncwarp();
+            float* cp = (float*)p.C + b * p.c_bstride + n00 + hh * 32 + lp * 4;
 #pragma unroll
-            for (int j = 0; j < 32; j++) if (n0 + j < p.N) cp[j] = __float2bfloat16_rn(f[j]);
+            for (int it = 0; it < 8; it++) {
+              const int rr = it * 4 + lr;
+              const uint4 ov = lds128(stg + (uint32_t)rr * 128 + (uint32_t)((lp ^ (rr & 7)) << 4));
+              const int64_t rg = row_base + rr;
+              if (rg < p.M) *reinterpret_cast<uint4*>(cp + rg * p.ldc) = ov;
+            }
+            __syncwarp();
+          }
+        } else if (row_ok) {                                // N tail / unaligned leading dimension: scalar path
+          const int64_t co = b * p.c_bstride + row * p.ldc + n00;
+#pragma unroll
+          for (int j = 0; j < 64; j++) {
+            if (n00 + j < p.N) {
+              if (p.c_f32) ((float*)p.C)[co + j] = f[j];
+              else ((bf16*)p.C)[co + j] = __float2bfloat16_rn(f[j]);
+            }
           }
         }
-      };
-
-#pragma unroll 1
-      for (int c = 0; c < NCH; c += 2) {
-        uint4 rq0[4], rq1[4];
-        bool have0 = false, have1 = false;
-        if (res_bf16_fast && row_ok) {                 // residual rows do not depend on the accumulator: fetch first
-          const int64_t n00 = ntile0 + half * COLS_PER_WARP + c * 32;
-          const bf16* rp = (const bf16*)p.residual + b * p.res_bstride + row * p.ldres + n00;
-          have0 = n00 + 32 <= p.N;
-          have1 = n00 + 64 <= p.N;
-          if (have0) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) rq0[j] = *reinterpret_cast<const uint4*>(rp + j * 8);
-          }
-          if (have1) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) rq1[j] = *reinterpret_cast<const uint4*>(rp + 32 + j * 8);
-          }
-        }
-        uint32_t v0[32], v1[32];
-        __syncwarp();                                  // tcgen05.ld is .sync.aligned: reconverge first
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * COLS_PER_WARP + c * 32);
-        tmem_ld_32x32b_x32(taddr, v0);
-        tmem_ld_32x32b_x32(taddr + 32, v1);
-        tmem_ld_wait();
-        finish(c, v0, rq0, have0);
-        finish(c + 1, v1, rq1, have1);
       }
       // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator back
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_leader(tempty_bar(acc));   // the leader's MMA thread waits for both CTAs' epilogues
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if constexpr (PAIR) cluster_sync_all();      // no CTA may exit (or free TMEM) while its peer can still signal it
+  else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -441,20 +541,33 @@ static int make_map_2d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t
   return CIR_OK;
 }
 
-template <int BN>
-static int launch_tc(cir_ctx* ctx, const cir_gemm_args* a, const tc::Params& p, const CUtensorMap& ma, const CUtensorMap& mw) {
-  using C = tc::Cfg<BN>;
+template <int BN, bool PAIR>
+static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, const CUtensorMap& mw) {
+  using C = tc::Cfg<BN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    CIR_CUDA(cudaFuncSetAttribute(tc::gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CIR_CUDA(cudaFuncSetAttribute(tc::gemm_tcgen05_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  int grid = p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms;
+  const int slots = PAIR ? ctx->num_sms / 2 : ctx->num_sms;
+  const int workers = p.num_tiles < slots ? p.num_tiles : slots;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(PAIR ? 2 * workers : workers);
+  cfg.blockDim = dim3(tc::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   cir_prof_gemm_begin(ctx, 2.0 * (double)p.M * (double)p.N * (double)p.K * (double)p.batch);
-  tc::gemm_tcgen05_kernel<BN><<<grid, tc::THREADS, C::SMEM_BYTES, ctx->stream>>>(ma, mw, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_tcgen05_kernel<BN, PAIR>, ma, mw, p);
   cir_prof_gemm_end(ctx);
+  if (e != cudaSuccess) { cir_set_error("tcgen05 GEMM launch failed: %s", cudaGetErrorString(e)); return CIR_ECUDA; }
   CIR_LAUNCH_CHECK(ctx);
-  (void)a;
   return CIR_OK;
 }
 
@@ -476,11 +589,15 @@ int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a) {
   const int64_t a_rows = p.a_rows_per_batch * (a->batch - 1) + a->M;
   const int64_t w_rows = p.w_rows_per_batch * (a->batch - 1) + a->N;
   CIR_CHECK_ARG(a_rows < (1ll << 31) && w_rows < (1ll << 31), "tcgen05 GEMM: too many rows for a 32-bit TMA coordinate");
-  // small problems: narrower N tile so the persistent grid still covers the SMs
+  // large problems: 256 x 256 CTA-pair tiles (cta_group::2); small ones: single-CTA tiles, narrower when
+  // that is what it takes for the persistent grid to cover the SMs
   const int64_t tiles256 = ((a->M + tc::BM - 1) / tc::BM) * ((a->N + 255) / 256) * a->batch;
-  const bool use128 = (a->N <= 128) || (tiles256 < ctx->num_sms);
+  const int64_t pair_tiles = ((a->M + 2 * tc::BM - 1) / (2 * tc::BM)) * ((a->N + 255) / 256) * a->batch;
+  const bool use_pair = ctx->gemm_pair && pair_tiles >= ctx->num_sms / 2;
+  const bool use128 = !use_pair && ((a->N <= 128) || (tiles256 < ctx->num_sms));
   const int BN = use128 ? 128 : 256;
-  p.m_blocks = (int32_t)((a->M + tc::BM - 1) / tc::BM);
+  const int tile_m = use_pair ? 2 * tc::BM : tc::BM;
+  p.m_blocks = (int32_t)((a->M + tile_m - 1) / tile_m);
   p.n_blocks = (int32_t)((a->N + BN - 1) / BN);
   p.k_blocks = (int32_t)((a->K + tc::BK - 1) / tc::BK);
   const int64_t nt = (int64_t)p.m_blocks * p.n_blocks * a->batch;
@@ -488,7 +605,8 @@ int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a) {
   p.num_tiles = (int32_t)nt;
   CUtensorMap ma, mw;
   CIR_TRY(make_map_2d(ctx, &ma, a->A, a_rows, a->K, a->lda, tc::BM));
-  CIR_TRY(make_map_2d(ctx, &mw, a->W, w_rows, a->K, a->ldw, BN));
-  if (use128) return launch_tc<128>(ctx, a, p, ma, mw);
-  return launch_tc<256>(ctx, a, p, ma, mw);
+  CIR_TRY(make_map_2d(ctx, &mw, a->W, w_rows, a->K, a->ldw, use_pair ? BN / 2 : BN));
+  if (use_pair) return launch_tc<256, true>(ctx, p, ma, mw);
+  if (use128) return launch_tc<128, false>(ctx, p, ma, mw);
+  return launch_tc<256, false>(ctx, p, ma, mw);
 }

@@ -66,6 +66,7 @@ extern "C" int cir_create(cir_ctx** out, int device, int dtype) {
   c->dtype = dtype;
   c->gemm_impl = CIR_GEMM_AUTO;
   c->attn_impl = 0;
+  c->gemm_pair = 1;
   c->stream = 0;
   c->num_sms = prop.multiProcessorCount;
   c->launches = 0;
@@ -103,9 +104,10 @@ extern "C" int cir_profile_gemm_read(cir_ctx* ctx, double* total_ms, double* tot
 }
 extern "C" int cir_set_stream(cir_ctx* ctx, void* s) { ctx->stream = (cudaStream_t)s; return CIR_OK; }
 extern "C" int cir_set_gemm_impl(cir_ctx* ctx, int impl) {
-  CIR_CHECK_ARG(impl >= CIR_GEMM_AUTO && impl <= CIR_GEMM_TCGEN05, "bad gemm impl %d", impl);
-  CIR_CHECK_ARG(!(impl == CIR_GEMM_TCGEN05 && ctx->dtype != CIR_DTYPE_BF16), "tcgen05 GEMM needs a bf16 context");
-  ctx->gemm_impl = impl;
+  CIR_CHECK_ARG(impl >= CIR_GEMM_AUTO && impl <= CIR_GEMM_TCGEN05_1CTA, "bad gemm impl %d", impl);
+  CIR_CHECK_ARG(!(impl >= CIR_GEMM_TCGEN05 && ctx->dtype != CIR_DTYPE_BF16), "tcgen05 GEMM needs a bf16 context");
+  ctx->gemm_pair = impl == CIR_GEMM_TCGEN05_1CTA ? 0 : 1;
+  ctx->gemm_impl = impl == CIR_GEMM_TCGEN05_1CTA ? CIR_GEMM_TCGEN05 : impl;
   return CIR_OK;
 }
 extern "C" int cir_set_attention_impl(cir_ctx* ctx, int impl) {

@@ -43,6 +43,7 @@ extern "C" {
 #define CIR_GEMM_AUTO    0    /* bf16 -> tcgen05, fp32 -> simt */
 #define CIR_GEMM_SIMT    1    /* force the CUDA-core GEMM (debug / cross-check) */
 #define CIR_GEMM_TCGEN05 2
+#define CIR_GEMM_TCGEN05_1CTA 3   /* tcgen05 but never the cta_group::2 pair tile (cross-check) */
 
 #define CIR_ACT_NONE 0
 #define CIR_ACT_GELU 1        /* erf GELU (transformers ACT2FN["gelu"], nn.GELU) */

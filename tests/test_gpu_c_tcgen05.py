@@ -39,6 +39,10 @@ SHAPES = [
     (96, 200, 128, 1),      # N tail not a multiple of 32
     (40, 100, 64, 3),       # tiny batched
     (3, 256, 768, 1),       # stage-I projection (M=3)
+    (5000, 768, 768, 2),    # cta_group::2 pair tiles (>= 74 pair tiles), batch folding, M tail inside a pair
+    (4100, 2304, 768, 1),   # pair tiles, odd number of 128-row blocks (peer CTA fully out of range on the last tile)
+    (19000, 3072, 768, 1),  # pair tiles, several tiles per CTA pair (persistent loop + accumulator double buffering)
+    (9500, 768, 3072, 1),   # pair tiles, long K (ring wraps many times)
 ]
 
 
@@ -76,6 +80,21 @@ def test_tcgen05_epilogues(e16):
         e16.set_gemm_impl(N_.GEMM_AUTO)
         tol = 2e-3 if out.dtype == torch.float32 else 3e-2
         assert (out.double() - want).abs().max() < tol * max(1.0, want.abs().max().item()), kw
+
+
+def test_pair_tile_matches_single_cta_and_epilogues(e16):
+    M, N, K = 3300, 768, 768
+    A = _rand(2, M, K, seed=1).bfloat16()
+    W = _rand(2, N, K, seed=2, scale=0.05).bfloat16()
+    bias = _rand(2, N, seed=3)
+    res16 = _rand(2, M, N, seed=4).bfloat16()
+    for kw in (dict(out_f32=True), dict(act=N_.ACT_GELU), dict(residual=res16, out_f32=True), dict(residual=res16)):
+        e16.set_gemm_impl(N_.GEMM_TCGEN05)
+        pair = e16.gemm(A, W, bias, **kw)
+        e16.set_gemm_impl(N_.GEMM_TCGEN05_1CTA)
+        single = e16.gemm(A, W, bias, **kw)
+        e16.set_gemm_impl(N_.GEMM_AUTO)
+        assert torch.equal(pair, single), kw          # same MMA order along K -> bit-identical
 
 
 def test_tcgen05_shared_a_and_strided_rows(e16):
