@@ -310,6 +310,10 @@ extern "C" int cir_attention(cir_ctx* ctx, const cir_attn_args* a) {
   if (a->B == 0 || a->Lq == 0) return CIR_OK;
   CIR_CHECK_ARG(a->Lk >= 1 && a->Lk <= 1024, "attention: Lk=%d out of range [1,1024]", a->Lk);
   CIR_CHECK_ARG(a->H >= 1 && a->H <= 65535, "attention: bad head count %d", a->H);
+  if (ctx->dtype == CIR_DTYPE_BF16 && ctx->attn_impl == 0) {
+    const int rc = cir_attention_tc(ctx, a);          // tcgen05/TMEM kernel where the shape is eligible
+    if (rc != CIR_EUNSUPPORTED) return rc;
+  }
   if (ctx->dtype == CIR_DTYPE_BF16 && ctx->attn_impl != 1) {
     // tensor-core path: needs 4-byte aligned rows for the packed loads/stores and 16 B aligned K/V rows
     CIR_CHECK_ARG((a->q_rs % 2) == 0 && (a->o_rs % 2) == 0 && (a->q_bs % 2) == 0 && (a->o_bs % 2) == 0 &&

@@ -91,3 +91,6 @@ __device__ __forceinline__ float warp_max(float v) {
 // internal cross-file entry points
 int cir_gemm_simt(cir_ctx* ctx, const cir_gemm_args* a);
 int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a);
+// 2-D bf16 tensor map over a [rows, K] row-major matrix (row stride ld elements), box [box_rows, 64], SWIZZLE_128B
+int cir_make_map_2d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows);
+int cir_attention_tc(cir_ctx* ctx, const cir_attn_args* a);    // attention_tc.cu; CIR_EUNSUPPORTED -> caller falls back

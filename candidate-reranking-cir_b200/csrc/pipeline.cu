@@ -111,7 +111,7 @@ extern "C" int cir_set_gemm_impl(cir_ctx* ctx, int impl) {
   return CIR_OK;
 }
 extern "C" int cir_set_attention_impl(cir_ctx* ctx, int impl) {
-  CIR_CHECK_ARG(impl == 0 || impl == 1, "bad attention impl %d", impl);
+  CIR_CHECK_ARG(impl >= 0 && impl <= 2, "bad attention impl %d", impl);
   ctx->attn_impl = impl;
   return CIR_OK;
 }
@@ -206,6 +206,7 @@ extern "C" int cir_vit_forward(cir_ctx* ctx, const cir_vit_weights* w, const flo
     a.q_bs = a.k_bs = a.v_bs = N * 3 * D; a.q_rs = a.k_rs = a.v_rs = 3 * D;
     a.o_bs = N * D; a.o_rs = D;
     a.B = (int32_t)B; a.H = CIR_HEADS; a.Lq = (int32_t)N; a.Lk = (int32_t)N; a.scale = 0.125f;                   // head_dim ** -0.5 (:50)
+    a.kv_batches = (int32_t)B;
     CIR_TRY(cir_attention(ctx, &a));
     CIR_TRY(gemm(ctx, ws.ctx, D, 0, w->proj_w[i], D, 0, w->proj_b[i], 0, ws.x, D, 0, 1, ws.x, D, 0, 1, R, D, D, 1, CIR_ACT_NONE));
     // x = x + fc2(gelu(fc1(norm2(x))))   (src/vit.py:109, :35-41)
@@ -279,6 +280,7 @@ extern "C" int cir_stage1_encode(cir_ctx* ctx, const cir_stage1_weights* w, cons
     c.q = ws.qc; c.k = ws.kv; c.v = at(ws.kv, D, es); c.o = ws.ctx;
     c.q_bs = L * D; c.q_rs = D; c.k_bs = c.v_bs = N * 2 * D; c.k_rs = c.v_rs = 2 * D; c.o_bs = L * D; c.o_rs = D;
     c.B = (int32_t)Q; c.H = CIR_HEADS; c.Lq = (int32_t)L; c.Lk = (int32_t)N; c.scale = 0.125f;
+    c.kv_batches = (int32_t)Q;
     CIR_TRY(cir_attention(ctx, &c));
     CIR_TRY(gemm(ctx, ws.ctx, D, 0, w->cross_out_w[i], D, 0, w->cross_out_b[i], 0, ws.pre, D, 0, 1, ws.a, D, 0, 0, R, D, D, 1, CIR_ACT_NONE));
     CIR_TRY(cir_add_layernorm(ctx, ws.pre, 1, R, nullptr, w->cross_ln_g[i], w->cross_ln_b[i], R, ws.x, 0, R, BERT_EPS));
@@ -333,6 +335,7 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
                                 const int32_t* mask, int64_t Q, int64_t L, int64_t N,
                                 const int32_t* trip_query, const int32_t* trip_slot, int64_t T,
                                 const int32_t* attn_work, int64_t num_attn_work,
+                                const int32_t* attn_tiles, int64_t num_attn_tiles,
                                 float* scores, float* feats, void* workspace, size_t workspace_bytes) {
   if (T == 0) return CIR_OK;
   CIR_CHECK_ARG(C >= 1 && Q >= 1, "stage2: need at least one candidate and one query");
@@ -379,6 +382,7 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
       c.q_bs = L * D; c.q_rs = D; c.k_bs = c.v_bs = N * 4 * D; c.k_rs = c.v_rs = 4 * D; c.o_bs = L * 2 * D; c.o_rs = 2 * D;
       c.kv_index = trip_slot;
       c.work = attn_work; c.num_work = (int32_t)num_attn_work;
+      c.tiles = attn_tiles; c.num_tiles = (int32_t)num_attn_tiles; c.kv_batches = (int32_t)C;
       c.B = (int32_t)T; c.H = CIR_HEADS; c.Lq = (int32_t)L; c.Lk = (int32_t)N; c.scale = 0.125f;
       CIR_TRY(cir_attention(ctx, &c));
     }

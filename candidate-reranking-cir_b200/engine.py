@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import native as N
-from .schedule import build_attn_work, plan_chunks
+from .schedule import build_attn_tiles, build_attn_work, plan_chunks
 
 HIDDEN, FFN, LAYERS, EMBED = 768, 3072, 12, 256
 NEG_FILL = -99999.99          # src/validate_stage2.py:123,258
@@ -49,7 +49,7 @@ class Engine:
         N.check(self._lib.cir_set_gemm_impl(self.ctx, impl), "cir_set_gemm_impl")
 
     def set_attention_impl(self, impl: int):
-        """0 = auto (mma.sync tensor cores in bf16 mode), 1 = CUDA-core kernel (cross-check)."""
+        """0 = auto (tcgen05 where eligible, else mma.sync), 1 = CUDA-core kernel, 2 = mma.sync only."""
         N.check(self._lib.cir_set_attention_impl(self.ctx, impl), "cir_set_attention_impl")
 
     def profile_gemm(self, enable: bool):
@@ -271,7 +271,7 @@ class Engine:
         return out
 
     def stage2_score_chunk(self, w, gallery_tokens, cand_list, z_t, ids, mask, trip_query, trip_slot, want_feats=False,
-                           attn_work=None):
+                           attn_work=None, attn_tiles=None):
         """One C-ABI call: T triplets sharing C candidates -> (scores fp32 [T], feats fp32 [T,1536] | None).
         ``attn_work``: optional int32 [W,4] K/V-sharing work list (schedule.build_attn_work)."""
         cand_list, ids, mask = self._i32(cand_list), self._i32(ids), self._i32(mask)
@@ -284,11 +284,12 @@ class Engine:
         need = self._lib.cir_stage2_workspace_bytes(self.ctx, T, Cn, Q, L, n_tok)
         ws = self.workspace(need)
         aw = None if attn_work is None or len(attn_work) == 0 else self._i32(attn_work)
+        at = None if attn_tiles is None or len(attn_tiles) == 0 else self._i32(attn_tiles)
         self._sync_stream()
         N.check(self._lib.cir_stage2_score(
             self.ctx, C.byref(w), N.ptr(gallery_tokens), N.ptr(cand_list), Cn, N.ptr(z_t), N.ptr(ids), N.ptr(mask),
             Q, L, n_tok, N.ptr(trip_query), N.ptr(trip_slot), T, N.ptr(aw), 0 if aw is None else aw.shape[0],
-            N.ptr(scores), N.ptr(feats), N.ptr(ws), ws.numel()),
+            N.ptr(at), 0 if at is None else at.shape[0], N.ptr(scores), N.ptr(feats), N.ptr(ws), ws.numel()),
             "cir_stage2_score")
         return scores, feats
 
@@ -305,7 +306,8 @@ class Engine:
             ql = torch.from_numpy(ch.query_list.astype(np.int64)).to(self.device)
             s, _ = self.stage2_score_chunk(w, gallery_tokens, ch.cand_list, z_t.index_select(0, ql).contiguous(),
                                            ids_d.index_select(0, ql), mask_d.index_select(0, ql), ch.trip_query, ch.trip_slot,
-                                           attn_work=build_attn_work(ch.trip_slot, ids_d.shape[1]))
+                                           attn_work=build_attn_work(ch.trip_slot, ids_d.shape[1]),
+                                           attn_tiles=build_attn_tiles(ch.trip_slot, ids_d.shape[1]))
             out.index_copy_(0, torch.from_numpy(ch.flat_pos).to(self.device), s)
         return out.view(Q, K)
 
@@ -396,7 +398,7 @@ class Engine:
         N.check(self._lib.cir_gemm(self.ctx, C.byref(g)), "cir_gemm")
         return Cm if batched else Cm[0]
 
-    def attention(self, q, k, v, key_mask=None, kv_index=None, scale=0.125, work=None):
+    def attention(self, q, k, v, key_mask=None, kv_index=None, scale=0.125, work=None, tiles=None):
         """q [B,Lq,H*64], k/v [Bk,Lk,H*64] act dtype -> o [B,Lq,H*64]; test hook over cir_attention."""
         B, Lq, HD = q.shape
         Lk = k.shape[1]
@@ -411,6 +413,8 @@ class Engine:
         a.key_mask, a.kv_index, a.mask_index = N.ptr(km), N.ptr(ki), N.vp(0)
         wk = None if work is None else self._i32(work)
         a.work, a.num_work = N.ptr(wk), (0 if wk is None else wk.shape[0])
+        tl = None if tiles is None else self._i32(tiles)
+        a.tiles, a.num_tiles, a.kv_batches = N.ptr(tl), (0 if tl is None else tl.shape[0]), k.shape[0]
         a.B, a.H, a.Lq, a.Lk, a.scale = B, HD // 64, Lq, Lk, scale
         self._sync_stream()
         N.check(self._lib.cir_attention(self.ctx, C.byref(a)), "cir_attention")

@@ -39,6 +39,7 @@ class AttnArgs(C.Structure):
                 ("q_bs", i64), ("q_rs", i64), ("k_bs", i64), ("k_rs", i64),
                 ("v_bs", i64), ("v_rs", i64), ("o_bs", i64), ("o_rs", i64),
                 ("kv_index", vp), ("key_mask", vp), ("mask_index", vp), ("work", vp), ("num_work", i32),
+                ("tiles", vp), ("num_tiles", i32), ("kv_batches", i32),
                 ("B", i32), ("H", i32), ("Lq", i32), ("Lk", i32), ("scale", C.c_float)]
 
 
@@ -105,7 +106,7 @@ _SIGS = {
     "cir_stage1_encode": (C.c_int, [vp, C.POINTER(Stage1Weights), vp, vp, vp, vp, i64, i64, i64, vp, vp, C.c_int, vp, C.c_size_t]),
     "cir_stage1_gallery_embed": (C.c_int, [vp, C.POINTER(Stage1Weights), vp, i64, i64, vp, vp, C.c_size_t]),
     "cir_stage2_workspace_bytes": (C.c_size_t, [vp, i64, i64, i64, i64, i64]),
-    "cir_stage2_score": (C.c_int, [vp, C.POINTER(Stage2Weights), vp, vp, i64, vp, vp, vp, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, vp, C.c_size_t]),
+    "cir_stage2_score": (C.c_int, [vp, C.POINTER(Stage2Weights), vp, vp, i64, vp, vp, vp, i64, i64, i64, vp, vp, i64, vp, i64, vp, i64, vp, vp, vp, C.c_size_t]),
 }
 
 _lib = None

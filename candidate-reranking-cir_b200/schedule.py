@@ -107,6 +107,40 @@ def build_attn_work(trip_slot: np.ndarray, L: int, warps: int = 8) -> np.ndarray
     return out
 
 
+def build_attn_tiles(trip_slot: np.ndarray, L: int) -> np.ndarray:
+    """Tile list for the tcgen05 attention kernel (``cir_attn_args.tiles``): int32 [W,4] =
+    (first triplet, triplets in the tile, first query row, rows per triplet RB).  A tile is 128 query
+    rows: 128/RB consecutive triplets of ONE candidate run (RB = 32 or 64), or a 128-row slice of a
+    single triplet when L > 64."""
+    trip_slot = np.asarray(trip_slot)
+    if trip_slot.size == 0:
+        return np.zeros((0, 4), np.int32)
+    assert np.all(np.diff(trip_slot) >= 0), "trip_slot must be candidate-major (sorted)"
+    if L > 64:
+        nslices = (L + 127) // 128
+        t = np.repeat(np.arange(trip_slot.size), nslices)
+        out = np.zeros((t.size, 4), np.int32)
+        out[:, 0] = t
+        out[:, 1] = 1
+        out[:, 2] = np.tile(np.arange(nslices) * 128, trip_slot.size)
+        out[:, 3] = 128
+        return out
+    RB = 32 if L <= 32 else 64
+    G = 128 // RB
+    starts = np.flatnonzero(np.r_[True, trip_slot[1:] != trip_slot[:-1]])
+    counts = np.diff(np.r_[starts, trip_slot.size])
+    ntiles = (counts + G - 1) // G
+    run_of = np.repeat(np.arange(starts.size), ntiles)
+    first = np.cumsum(ntiles) - ntiles
+    g0 = (np.arange(run_of.size) - first[run_of]) * G
+    out = np.zeros((run_of.size, 4), np.int32)
+    out[:, 0] = starts[run_of] + g0
+    out[:, 1] = np.minimum(G, counts[run_of] - g0)
+    out[:, 2] = 0
+    out[:, 3] = RB
+    return out
+
+
 def shard_rows(num_rows: int, rank: int, world: int) -> slice:
     """Contiguous block partition of ``num_rows`` units over ``world`` ranks (first ranks get the
     remainder).  Used for queries (stage II) and gallery rows (stage I)."""

@@ -65,7 +65,7 @@ int  cir_create(cir_ctx** out, int device, int dtype);
 int  cir_destroy(cir_ctx* ctx);
 int  cir_set_stream(cir_ctx* ctx, void* cuda_stream);       /* cudaStream_t */
 int  cir_set_gemm_impl(cir_ctx* ctx, int impl);              /* CIR_GEMM_* */
-int  cir_set_attention_impl(cir_ctx* ctx, int impl);      /* 0 auto (mma tensor cores in bf16), 1 CUDA-core kernel */
+int  cir_set_attention_impl(cir_ctx* ctx, int impl);      /* 0 auto (tcgen05 where eligible, else mma.sync), 1 CUDA-core kernel, 2 mma.sync only */
 int  cir_get_dtype(const cir_ctx* ctx);
 /* number of kernel launches issued through this context since the last reset (bench.py's gpu_launches) */
 int64_t cir_launch_count(cir_ctx* ctx, int reset);
@@ -120,6 +120,11 @@ typedef struct cir_attn_args {
    * major triplets).  A unit is (batch, 16-row query tile): unit u -> batch first+u/mt, tile u%mt,
    * mt = ceil(Lq/16).  NULL: every batch is its own run. */
   const int32_t* work; int32_t num_work;
+  /* tcgen05 path (bf16, no key_mask): optional tile list int32 [num_tiles][4] = {first batch, batches in
+   * the tile, first query row, rows per batch RB in {32,64,128}}: a tile is 128 query rows = (128/RB)
+   * batches sharing one K/V batch x RB rows starting at `first query row`.  NULL: one batch per tile.
+   * kv_batches = number of K/V batches behind k/v (rows = kv_batches*Lk, k_bs must equal Lk*k_rs). */
+  const int32_t* tiles; int32_t num_tiles; int32_t kv_batches;
   int32_t B, H, Lq, Lk;
   float scale;
 } cir_attn_args;
@@ -254,8 +259,9 @@ typedef struct cir_stage2_weights {
  *   gallery_tokens act [G,N,768]; cand_list int32 [C] gallery rows of the chunk's candidates
  *   z_t act [Q,L,768]; ids/mask int32 [Q,L]
  *   trip_query int32 [T] -> row of z_t/ids/mask; trip_slot int32 [T] -> position in cand_list
- *   attn_work int32 [W,4] optional cross-attention work list (see cir_attn_args.work; requires trip_slot
- *   sorted so that triplets naming the same candidate are adjacent)
+ *   attn_work int32 [W,4] / attn_tiles int32 [W',4] optional cross-attention work lists (see
+ *   cir_attn_args.work / .tiles; both require trip_slot sorted so that triplets naming the same candidate
+ *   are adjacent)
  *   scores fp32 [T] (class-0 logit); feats fp32 [T,1536] optional (cat(CLS0,CLS1), nlvr_encoder.py:909) */
 size_t cir_stage2_workspace_bytes(const cir_ctx* ctx, int64_t T, int64_t C, int64_t Q, int64_t L, int64_t N);
 int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const void* gallery_tokens,
@@ -263,6 +269,7 @@ int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const void* gall
                      const int32_t* mask, int64_t Q, int64_t L, int64_t N,
                      const int32_t* trip_query, const int32_t* trip_slot, int64_t T,
                      const int32_t* attn_work, int64_t num_attn_work,
+                     const int32_t* attn_tiles, int64_t num_attn_tiles,
                      float* scores, float* feats, void* workspace, size_t workspace_bytes);
 
 #ifdef __cplusplus

@@ -207,3 +207,24 @@ def test_attention_mma_vs_reference(e16, B, Lq, Lk, masked):
     finally:
         e16.set_attention_impl(0)
     assert (o.float() - o3.float()).abs().max() < 2.5e-2
+
+
+@pytest.mark.parametrize("B,Lq,Lk", [(9, 32, 577), (5, 12, 577), (6, 40, 577), (3, 577, 577), (7, 32, 128), (4, 32, 200), (2, 130, 65)])
+def test_attention_tcgen05_vs_reference(e16, B, Lq, Lk):
+    q = _rand(B, Lq, 768, seed=1).bfloat16()
+    nkv = 3
+    k = _rand(nkv, Lk, 768, seed=2).bfloat16()
+    v = _rand(nkv, Lk, 768, seed=3).bfloat16()
+    kv_index = torch.tensor(sorted(i % nkv for i in range(B)), dtype=torch.int32).cuda()
+    ref = ref_attention(q, k, v, None, kv_index)
+    tiles = cir.schedule.build_attn_tiles(kv_index.cpu().numpy(), Lq)
+    n0 = e16.launch_count()
+    o = e16.attention(q, k, v, kv_index=kv_index, tiles=tiles)                 # tcgen05 kernel
+    err = (o.float() - ref).abs().max().item()
+    assert err < 2.5e-2, err
+    e16.set_attention_impl(2)
+    try:
+        o2 = e16.attention(q, k, v, kv_index=kv_index, work=cir.schedule.build_attn_work(kv_index.cpu().numpy(), Lq))
+    finally:
+        e16.set_attention_impl(0)
+    assert (o.float() - o2.float()).abs().max() < 2.5e-2

@@ -117,3 +117,20 @@ def test_build_attn_work_units():
                 covered.add((t, mi))
         assert covered == {(t, mi) for t in range(len(slot)) for mi in range(mt)}
     assert sched.build_attn_work(np.zeros(0, np.int32), 32).shape == (0, 4)
+
+
+def test_build_attn_tiles_cover():
+    from importlib import import_module
+    sched = import_module("candidate-reranking-cir_b200.schedule")
+    slot = np.array([0, 0, 0, 0, 0, 1, 3, 3, 3, 3, 3, 3, 3, 3, 3], np.int32)
+    for L in (12, 32, 40, 64, 100, 300):
+        tiles = sched.build_attn_tiles(slot, L)
+        rows = set()
+        for b0, nb, row0, RB in tiles.tolist():
+            assert nb * RB <= 128 and nb >= 1
+            assert len({slot[b0 + i] for i in range(nb)}) == 1
+            for i in range(nb):
+                for r in range(row0, min(row0 + RB, L)):
+                    assert (b0 + i, r) not in rows
+                    rows.add((b0 + i, r))
+        assert rows == {(t, r) for t in range(len(slot)) for r in range(L)}
