@@ -1,0 +1,91 @@
+"""world_size-2 gloo runs (CPU) of the multi-GPU host logic: sharding, padded all-gather, top-K merge.
+The per-rank compute is the CPU oracle here; on GPUs the same functions are driven by the engine
+(tests/test_gpu_e_multi.py, bench.py --gpus N)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import cir_b200 as cir
+from oracle import cir_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _merge_cpu(ds, is_):
+    """Reference merge: ascending distance, ties -> lowest global index (what cir_topk_merge does)."""
+    P, Q, K = ds.shape
+    d = ds.permute(1, 0, 2).reshape(Q, P * K)
+    i = is_.permute(1, 0, 2).reshape(Q, P * K).long()
+    key = torch.stack([torch.tensor(sorted(range(P * K), key=lambda c: (float(d[q, c]), int(i[q, c])))[:K]) for q in range(Q)])
+    return torch.gather(d, 1, key), torch.gather(i, 1, key).int()
+
+
+def _worker(rank, ws, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        D = cir.distributed
+        g = torch.Generator().manual_seed(0)
+        # ---- stage I: gallery sharded (uneven: 101 rows over 2 ranks), exclusion, merge
+        Q, G, K = 7, 101, 10
+        q = torch.nn.functional.normalize(torch.randn(Q, 256, generator=g), dim=-1)
+        gal = torch.nn.functional.normalize(torch.randn(G, 256, generator=g), dim=-1)
+        gal[60] = gal[3]                                       # tie across shards -> lowest global index wins
+        excl = torch.randint(0, G, (Q,), generator=g)
+
+        def local_topk(rows):
+            d, i = O.stage1_topk(q, gal[rows], None, min(K + 1, rows.stop - rows.start))
+            gi = i + rows.start
+            out_d = torch.full((Q, K), float("inf")); out_i = torch.full((Q, K), -1, dtype=torch.int32)
+            for r in range(Q):
+                keep = gi[r] != excl[r]
+                out_d[r, : min(K, int(keep.sum()))] = d[r][keep][:K]
+                out_i[r, : min(K, int(keep.sum()))] = gi[r][keep][:K].int()
+            return out_d, out_i
+        md, mi = D.sharded_stage1_topk(local_topk, _merge_cpu, G)
+        wd, wi = O.stage1_topk(q, gal, excl, K)
+        assert torch.equal(mi.long(), wi) and torch.equal(md, wd)
+        # ---- stage II: queries sharded (uneven: 5 rows over 2 ranks), padded all-gather
+        Qs, Ks = 5, 6
+        full = torch.randn(Qs, Ks, generator=g)
+        got = D.sharded_stage2_scores(lambda rows: full[rows].clone(), Qs)
+        assert torch.equal(got, full)
+        order = O.rerank_order(got)
+        assert torch.equal(order, O.rerank_order(full))
+        # empty shard: 1 query over 2 ranks
+        one = D.sharded_stage2_scores(lambda rows: full[:1][rows].clone(), 1)
+        assert torch.equal(one, full[:1])
+        ret[rank] = "ok"
+    except Exception as e:  # pragma: no cover
+        ret[rank] = f"{type(e).__name__}: {e}"
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_single_process_passthrough():
+    D = cir.distributed
+    x = torch.arange(12.0).view(4, 3)
+    assert torch.equal(D.sharded_stage2_scores(lambda rows: x[rows], 4), x)
+    d, i = D.sharded_stage1_topk(lambda rows: (x[:, :2], x[:, :2].int()), None, 10)
+    assert torch.equal(d, x[:, :2])
