@@ -36,6 +36,16 @@ constexpr int S_COL = 0, O_COL = 128;
 __host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int m, int n) { return make_idesc_bf16(m, n) | (1u << 16); }
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {       // one MUFU.EX2; exp2(-inf) = 0, denormal results flush to 0
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 __global__ void __launch_bounds__(THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, const cir_attn_args p,
@@ -172,18 +182,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_cons
       const int npieces = (n_pad + 31) >> 5;
       mbar_wait(sfull, (uint32_t)(j & 1));
       tcgen05_fence_after();
-      // ---- pass 1: row max over the valid keys of this chunk
+      // ---- pass 1: row max over the valid keys of this chunk (3-input FMNMX3; full chunks need no key test)
       float cmax = -INFINITY;
+      const bool full_chunk = keys == KC;
       for (int pc = 0; pc < npieces; pc++) {
         uint32_t v[32];
         __syncwarp();
         tmem_ld_32x32b_x32(lane_addr + S_COL + pc * 32, v);
         tmem_ld_wait();
+        if (full_chunk) {
 #pragma unroll
-        for (int i = 0; i < 32; i++) if (pc * 32 + i < keys) cmax = fmaxf(cmax, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 2) cmax = max3(cmax, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++) if (pc * 32 + i < keys) cmax = fmaxf(cmax, __uint_as_float(v[i]));
+        }
       }
       const float m_new = fmaxf(m, cmax * sl2);              // scale > 0: max commutes with the scaling
-      const float alpha = exp2f(m - m_new);                  // first chunk: exp2(-inf) = 0
+      const float alpha = ex2_approx(m - m_new);             // first chunk: exp2(-inf) = 0
       // ---- merge O_{j-1} (computed against the previous max) while the tensor core is idle anyway
       if (j > 0) {
         mbar_wait(ofull, (uint32_t)((j - 1) & 1));
@@ -211,12 +227,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_cons
         tmem_ld_32x32b_x32(lane_addr + S_COL + pc * 32, v);
         tmem_ld_wait();
         float pr[32];
+        if (full_chunk) {
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const float e = exp2f(fmaf(__uint_as_float(v[i]), sl2, -m));
-          pr[i] = (pc * 32 + i < keys) ? e : 0.f;
-          l += pr[i];
+          for (int i = 0; i < 32; i++) pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const float e = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m));
+            pr[i] = (pc * 32 + i < keys) ? e : 0.f;
+          }
         }
+        float ls = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i++) ls += pr[i];
+        l += ls;
         // keys pc*32 .. pc*32+31 -> atom (pc >> 1), 16 B pieces ((pc & 1) * 4 + 0..3) of row r
         uint8_t* prow = smem + OFF_P + (pc >> 1) * (128 * 128) + r * 128;
 #pragma unroll

@@ -271,8 +271,8 @@ extern "C" int cir_stage1_encode(cir_ctx* ctx, const cir_stage1_weights* w, cons
     a.q_bs = a.k_bs = a.v_bs = L * 3 * D; a.q_rs = a.k_rs = a.v_rs = 3 * D; a.o_bs = L * D; a.o_rs = D;
     a.key_mask = mask; a.B = (int32_t)Q; a.H = CIR_HEADS; a.Lq = (int32_t)L; a.Lk = (int32_t)L; a.scale = 0.125f;
     CIR_TRY(cir_attention(ctx, &a));
-    CIR_TRY(gemm(ctx, ws.ctx, D, 0, w->self_out_w[i], D, 0, w->self_out_b[i], 0, ws.pre, D, 0, 1, ws.h, D, 0, 0, R, D, D, 1, CIR_ACT_NONE));
-    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 1, R, nullptr, w->self_ln_g[i], w->self_ln_b[i], R, ws.a, 0, R, BERT_EPS));
+    CIR_TRY(gemm(ctx, ws.ctx, D, 0, w->self_out_w[i], D, 0, w->self_out_b[i], 0, ws.pre, D, 0, 0, ws.h, D, 0, 0, R, D, D, 1, CIR_ACT_NONE));
+    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 0, R, nullptr, w->self_ln_g[i], w->self_ln_b[i], R, ws.a, 0, R, BERT_EPS));
     // cross-attention onto the reference image tokens (all-ones encoder mask -> +0)
     CIR_TRY(gemm(ctx, ws.a, D, 0, w->cross_q_w[i], D, 0, w->cross_q_b[i], 0, ws.qc, D, 0, 0, nullptr, 0, 0, 0, R, D, D, 1, CIR_ACT_NONE));
     CIR_TRY(gemm(ctx, ws.reft, D, 0, w->cross_kv_w[i], D, 0, w->cross_kv_b[i], 0, ws.kv, 2 * D, 0, 0, nullptr, 0, 0, 0, Q * N, 2 * D, D, 1, CIR_ACT_NONE));
@@ -282,11 +282,11 @@ extern "C" int cir_stage1_encode(cir_ctx* ctx, const cir_stage1_weights* w, cons
     c.B = (int32_t)Q; c.H = CIR_HEADS; c.Lq = (int32_t)L; c.Lk = (int32_t)N; c.scale = 0.125f;
     c.kv_batches = (int32_t)Q;
     CIR_TRY(cir_attention(ctx, &c));
-    CIR_TRY(gemm(ctx, ws.ctx, D, 0, w->cross_out_w[i], D, 0, w->cross_out_b[i], 0, ws.pre, D, 0, 1, ws.a, D, 0, 0, R, D, D, 1, CIR_ACT_NONE));
-    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 1, R, nullptr, w->cross_ln_g[i], w->cross_ln_b[i], R, ws.x, 0, R, BERT_EPS));
+    CIR_TRY(gemm(ctx, ws.ctx, D, 0, w->cross_out_w[i], D, 0, w->cross_out_b[i], 0, ws.pre, D, 0, 0, ws.a, D, 0, 0, R, D, D, 1, CIR_ACT_NONE));
+    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 0, R, nullptr, w->cross_ln_g[i], w->cross_ln_b[i], R, ws.x, 0, R, BERT_EPS));
     CIR_TRY(gemm(ctx, ws.x, D, 0, w->ffn1_w[i], D, 0, w->ffn1_b[i], 0, ws.f, F, 0, 0, nullptr, 0, 0, 0, R, F, D, 1, CIR_ACT_GELU));
-    CIR_TRY(gemm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.pre, D, 0, 1, ws.x, D, 0, 0, R, D, F, 1, CIR_ACT_NONE));
-    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 1, R, nullptr, w->ffn_ln_g[i], w->ffn_ln_b[i], R, ws.h, 0, R, BERT_EPS));
+    CIR_TRY(gemm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.pre, D, 0, 0, ws.x, D, 0, 0, R, D, F, 1, CIR_ACT_NONE));
+    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 0, R, nullptr, w->ffn_ln_g[i], w->ffn_ln_b[i], R, ws.h, 0, R, BERT_EPS));
   }
   if (z_t) CIR_TRY(cir_gather_rows(ctx, ws.h, nullptr, z_t, R, D));                                               // return_raw=True
   if (q_emb) CIR_TRY(project_normalize(ctx, ws.h, L * D, w->text_proj_w, w->text_proj_b, Q, ws.proj, q_emb, normalize_twice));  // blip_stage1.py:83
@@ -366,9 +366,9 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
       CIR_TRY(cir_attention(ctx, &a));
     }
     // a_s = LayerNorm{A,B}(dense_s(ctx_s) + h_s)   (:261-264)
-    CIR_TRY(gemm(ctx, ws.ctx, D, M * D, w->self_out_w[i], D, D * D, w->self_out_b[i], D, ws.pre, D, M * D, 1, ws.h, D, M * D, 0,
+    CIR_TRY(gemm(ctx, ws.ctx, D, M * D, w->self_out_w[i], D, D * D, w->self_out_b[i], D, ws.pre, D, M * D, 0, ws.h, D, M * D, 0,
                  M, D, D, 2, CIR_ACT_NONE));
-    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 1, 2 * M, nullptr, w->self_ln_g[i], w->self_ln_b[i], M, ws.a, 0, 2 * M, BERT_EPS));
+    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 0, 2 * M, nullptr, w->self_ln_g[i], w->self_ln_b[i], M, ws.a, 0, 2 * M, BERT_EPS));
     // ---- twin cross-attention onto the SAME candidate tokens (:322-339)
     CIR_TRY(gemm(ctx, ws.a, D, M * D, w->cross_q_w[i], D, D * D, w->cross_q_b[i], D, ws.qc, D, M * D, 0, nullptr, 0, 0, 0,
                  M, D, D, 2, CIR_ACT_NONE));
@@ -387,13 +387,13 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
       CIR_TRY(cir_attention(ctx, &c));
     }
     // m = merge(dense0(c0), dense1(c1)) folded into one K=1536 GEMM (:250-258); x_s = LayerNorm{A,B}(m + a_s) (:256,:260)
-    CIR_TRY(gemm(ctx, ws.ctxc, 2 * D, 0, w->cross_out_w[i], 2 * D, 0, w->cross_out_b[i], 0, ws.m, D, 0, 1, nullptr, 0, 0, 0,
+    CIR_TRY(gemm(ctx, ws.ctxc, 2 * D, 0, w->cross_out_w[i], 2 * D, 0, w->cross_out_b[i], 0, ws.m, D, 0, 0, nullptr, 0, 0, 0,
                  M, D, 2 * D, 1, CIR_ACT_NONE));
-    CIR_TRY(cir_add_layernorm(ctx, ws.m, 1, M, ws.a, w->cross_ln_g[i], w->cross_ln_b[i], M, ws.x, 0, 2 * M, BERT_EPS));
+    CIR_TRY(cir_add_layernorm(ctx, ws.m, 0, M, ws.a, w->cross_ln_g[i], w->cross_ln_b[i], M, ws.x, 0, 2 * M, BERT_EPS));
     // ---- FFN, weights shared by both streams (:469-476): both streams as 2M rows
     CIR_TRY(gemm(ctx, ws.x, D, 0, w->ffn1_w[i], D, 0, w->ffn1_b[i], 0, ws.f, F, 0, 0, nullptr, 0, 0, 0, 2 * M, F, D, 1, CIR_ACT_GELU));
-    CIR_TRY(gemm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.pre, D, 0, 1, ws.x, D, 0, 0, 2 * M, D, F, 1, CIR_ACT_NONE));
-    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 1, 2 * M, nullptr, w->ffn_ln_g[i], w->ffn_ln_b[i], 2 * M, ws.h, 0, 2 * M, BERT_EPS));
+    CIR_TRY(gemm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.pre, D, 0, 0, ws.x, D, 0, 0, 2 * M, D, F, 1, CIR_ACT_NONE));
+    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 0, 2 * M, nullptr, w->ffn_ln_g[i], w->ffn_ln_b[i], 2 * M, ws.h, 0, 2 * M, BERT_EPS));
   }
   // cat(CLS0, CLS1) (:909) -> cls_head (blip_stage2.py:50-54,134-136)
   CIR_TRY(cir_gather_cls(ctx, ws.h, T, L, ws.feats, feats));
