@@ -18,6 +18,7 @@ struct cir_ctx {
   int gemm_impl;        // CIR_GEMM_*
   int attn_impl;        // 0 = auto (tensor cores in bf16 mode), 1 = force the CUDA-core kernel
   int gemm_pair;        // 1 = allow cta_group::2 pair tiles for large GEMMs (default)
+  int prune_last;       // 1 = stage II computes the last layer for the CLS rows only (default)
   cudaStream_t stream;
   int num_sms;
   int64_t launches;

@@ -67,6 +67,7 @@ extern "C" int cir_create(cir_ctx** out, int device, int dtype) {
   c->gemm_impl = CIR_GEMM_AUTO;
   c->attn_impl = 0;
   c->gemm_pair = 1;
+  c->prune_last = 1;
   c->stream = 0;
   c->num_sms = prop.multiProcessorCount;
   c->launches = 0;
@@ -115,6 +116,7 @@ extern "C" int cir_set_attention_impl(cir_ctx* ctx, int impl) {
   ctx->attn_impl = impl;
   return CIR_OK;
 }
+extern "C" int cir_set_prune_last_layer(cir_ctx* ctx, int enable) { ctx->prune_last = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_get_dtype(const cir_ctx* ctx) { return ctx->dtype; }
 extern "C" int64_t cir_launch_count(cir_ctx* ctx, int reset) {
   int64_t n = ctx->launches;
@@ -336,6 +338,7 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
                                 const int32_t* trip_query, const int32_t* trip_slot, int64_t T,
                                 const int32_t* attn_work, int64_t num_attn_work,
                                 const int32_t* attn_tiles, int64_t num_attn_tiles,
+                                const int32_t* attn_tiles_cls, int64_t num_attn_tiles_cls,
                                 float* scores, float* feats, void* workspace, size_t workspace_bytes) {
   if (T == 0) return CIR_OK;
   CIR_CHECK_ARG(C >= 1 && Q >= 1, "stage2: need at least one candidate and one query");
@@ -352,7 +355,8 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
   CIR_TRY(cir_gather_rows(ctx, z_t, trip_query, ws.h, T, L * D));
   CIR_TRY(cir_gather_rows(ctx, ws.emb, trip_query, at(ws.h, M * D, es), T, L * D));
 
-  for (int i = 0; i < CIR_LAYERS; i++) {                                                                           // nlvr_encoder.py:506
+  const int full_layers = ctx->prune_last ? CIR_LAYERS - 1 : CIR_LAYERS;
+  for (int i = 0; i < full_layers; i++) {                                                                          // nlvr_encoder.py:506
     // ---- twin self-attention (:281-289, :346-363): separate weights per stream, shared padding mask (:774)
     CIR_TRY(gemm(ctx, ws.h, D, M * D, w->self_qkv_w[i], D, 3 * D * D, w->self_qkv_b[i], 3 * D, ws.qkv, 3 * D, M * 3 * D, 0,
                  nullptr, 0, 0, 0, M, 3 * D, D, 2, CIR_ACT_NONE));
@@ -395,8 +399,48 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
     CIR_TRY(gemm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.pre, D, 0, 0, ws.x, D, 0, 0, 2 * M, D, F, 1, CIR_ACT_NONE));
     CIR_TRY(cir_add_layernorm(ctx, ws.pre, 0, 2 * M, nullptr, w->ffn_ln_g[i], w->ffn_ln_b[i], 2 * M, ws.h, 0, 2 * M, BERT_EPS));
   }
+  if (ctx->prune_last) {
+    // ---- last layer, CLS rows only.  The encoder returns cat(h0[:,0,:], h1[:,0,:]) (nlvr_encoder.py:906-909), so
+    // in layer 11 only the query row 0 of each stream feeds the result; its keys/values still come from all L
+    // rows (self) and all N image tokens (cross).  Everything after the K/V projections runs on [2][T] rows.
+    const int i = CIR_LAYERS - 1;
+    CIR_TRY(gemm(ctx, ws.h, D, M * D, w->self_qkv_w[i], D, 3 * D * D, w->self_qkv_b[i], 3 * D, ws.qkv, 3 * D, M * 3 * D, 0,
+                 nullptr, 0, 0, 0, M, 3 * D, D, 2, CIR_ACT_NONE));
+    for (int s = 0; s < 2; s++) {
+      cir_attn_args a{};
+      void* qkv_s = at(ws.qkv, s * M * 3 * D, es);
+      a.q = qkv_s; a.k = at(qkv_s, D, es); a.v = at(qkv_s, 2 * D, es); a.o = at(ws.ctx, s * T * D, es);
+      a.q_bs = a.k_bs = a.v_bs = L * 3 * D; a.q_rs = a.k_rs = a.v_rs = 3 * D; a.o_bs = D; a.o_rs = D;
+      a.key_mask = mask; a.mask_index = trip_query;
+      a.B = (int32_t)T; a.H = CIR_HEADS; a.Lq = 1; a.Lk = (int32_t)L; a.scale = 0.125f;
+      CIR_TRY(cir_attention(ctx, &a));
+    }
+    CIR_TRY(gemm(ctx, ws.ctx, D, T * D, w->self_out_w[i], D, D * D, w->self_out_b[i], D, ws.pre, D, T * D, 0, ws.h, L * D, M * D, 0,
+                 T, D, D, 2, CIR_ACT_NONE));
+    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 0, 2 * T, nullptr, w->self_ln_g[i], w->self_ln_b[i], T, ws.a, 0, 2 * T, BERT_EPS));
+    CIR_TRY(gemm(ctx, ws.a, D, T * D, w->cross_q_w[i], D, D * D, w->cross_q_b[i], D, ws.qc, D, T * D, 0, nullptr, 0, 0, 0,
+                 T, D, D, 2, CIR_ACT_NONE));
+    CIR_TRY(gemm(ctx, ws.cand, D, 0, w->cross_kv_w[i], D, 0, w->cross_kv_b[i], 0, ws.kv, 4 * D, 0, 0, nullptr, 0, 0, 0,
+                 C * N, 4 * D, D, 1, CIR_ACT_NONE));
+    for (int s = 0; s < 2; s++) {
+      cir_attn_args c{};
+      c.q = at(ws.qc, s * T * D, es); c.k = at(ws.kv, s * 2 * D, es); c.v = at(ws.kv, s * 2 * D + D, es);
+      c.o = at(ws.ctxc, s * D, es);
+      c.q_bs = D; c.q_rs = D; c.k_bs = c.v_bs = N * 4 * D; c.k_rs = c.v_rs = 4 * D; c.o_bs = 2 * D; c.o_rs = 2 * D;
+      c.kv_index = trip_slot;
+      c.tiles = attn_tiles_cls; c.num_tiles = (int32_t)num_attn_tiles_cls; c.kv_batches = (int32_t)C;
+      c.B = (int32_t)T; c.H = CIR_HEADS; c.Lq = 1; c.Lk = (int32_t)N; c.scale = 0.125f;
+      CIR_TRY(cir_attention(ctx, &c));
+    }
+    CIR_TRY(gemm(ctx, ws.ctxc, 2 * D, 0, w->cross_out_w[i], 2 * D, 0, w->cross_out_b[i], 0, ws.m, D, 0, 0, nullptr, 0, 0, 0,
+                 T, D, 2 * D, 1, CIR_ACT_NONE));
+    CIR_TRY(cir_add_layernorm(ctx, ws.m, 0, T, ws.a, w->cross_ln_g[i], w->cross_ln_b[i], T, ws.x, 0, 2 * T, BERT_EPS));
+    CIR_TRY(gemm(ctx, ws.x, D, 0, w->ffn1_w[i], D, 0, w->ffn1_b[i], 0, ws.f, F, 0, 0, nullptr, 0, 0, 0, 2 * T, F, D, 1, CIR_ACT_GELU));
+    CIR_TRY(gemm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.pre, D, 0, 0, ws.x, D, 0, 0, 2 * T, D, F, 1, CIR_ACT_NONE));
+    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 0, 2 * T, nullptr, w->ffn_ln_g[i], w->ffn_ln_b[i], 2 * T, ws.h, 0, 2 * T, BERT_EPS));
+  }
   // cat(CLS0, CLS1) (:909) -> cls_head (blip_stage2.py:50-54,134-136)
-  CIR_TRY(cir_gather_cls(ctx, ws.h, T, L, ws.feats, feats));
+  CIR_TRY(cir_gather_cls(ctx, ws.h, T, ctx->prune_last ? 1 : L, ws.feats, feats));
   CIR_TRY(gemm(ctx, ws.feats, 2 * D, 0, w->cls0_w, 2 * D, 0, w->cls0_b, 0, ws.hid, D, 0, 1, nullptr, 0, 0, 0, T, D, 2 * D, 1, CIR_ACT_RELU));
   CIR_TRY(cir_head_dot(ctx, ws.hid, w->cls2_w, w->cls2_b, scores, T));
   return CIR_OK;

@@ -38,8 +38,8 @@ class Engine:
         N.check(self._lib.cir_create(C.byref(h), dev.index, N.DTYPE_BF16 if precision == "bf16" else N.DTYPE_F32), "cir_create")
         self.ctx = h
         self._ws: Optional[torch.Tensor] = None
-        self.max_triplets = 2048
-        self.max_candidates = 48
+        self.max_triplets = 4096
+        self.max_candidates = 64
 
     # ------------------------------------------------------------------ plumbing
     def _sync_stream(self):
@@ -51,6 +51,10 @@ class Engine:
     def set_attention_impl(self, impl: int):
         """0 = auto (tcgen05 where eligible, else mma.sync), 1 = CUDA-core kernel, 2 = mma.sync only."""
         N.check(self._lib.cir_set_attention_impl(self.ctx, impl), "cir_set_attention_impl")
+
+    def set_prune_last_layer(self, enable: bool):
+        """Stage II: layer 11 for the CLS rows only (default) or for all rows (cross-check)."""
+        N.check(self._lib.cir_set_prune_last_layer(self.ctx, 1 if enable else 0))
 
     def profile_gemm(self, enable: bool):
         N.check(self._lib.cir_profile_gemm(self.ctx, 1 if enable else 0))
@@ -271,7 +275,7 @@ class Engine:
         return out
 
     def stage2_score_chunk(self, w, gallery_tokens, cand_list, z_t, ids, mask, trip_query, trip_slot, want_feats=False,
-                           attn_work=None, attn_tiles=None):
+                           attn_work=None, attn_tiles=None, attn_tiles_cls=None):
         """One C-ABI call: T triplets sharing C candidates -> (scores fp32 [T], feats fp32 [T,1536] | None).
         ``attn_work``: optional int32 [W,4] K/V-sharing work list (schedule.build_attn_work)."""
         cand_list, ids, mask = self._i32(cand_list), self._i32(ids), self._i32(mask)
@@ -285,11 +289,12 @@ class Engine:
         ws = self.workspace(need)
         aw = None if attn_work is None or len(attn_work) == 0 else self._i32(attn_work)
         at = None if attn_tiles is None or len(attn_tiles) == 0 else self._i32(attn_tiles)
+        ac = None if attn_tiles_cls is None or len(attn_tiles_cls) == 0 else self._i32(attn_tiles_cls)
         self._sync_stream()
         N.check(self._lib.cir_stage2_score(
             self.ctx, C.byref(w), N.ptr(gallery_tokens), N.ptr(cand_list), Cn, N.ptr(z_t), N.ptr(ids), N.ptr(mask),
             Q, L, n_tok, N.ptr(trip_query), N.ptr(trip_slot), T, N.ptr(aw), 0 if aw is None else aw.shape[0],
-            N.ptr(at), 0 if at is None else at.shape[0], N.ptr(scores), N.ptr(feats), N.ptr(ws), ws.numel()),
+            N.ptr(at), 0 if at is None else at.shape[0], N.ptr(ac), 0 if ac is None else ac.shape[0], N.ptr(scores), N.ptr(feats), N.ptr(ws), ws.numel()),
             "cir_stage2_score")
         return scores, feats
 
@@ -307,7 +312,8 @@ class Engine:
             s, _ = self.stage2_score_chunk(w, gallery_tokens, ch.cand_list, z_t.index_select(0, ql).contiguous(),
                                            ids_d.index_select(0, ql), mask_d.index_select(0, ql), ch.trip_query, ch.trip_slot,
                                            attn_work=build_attn_work(ch.trip_slot, ids_d.shape[1]),
-                                           attn_tiles=build_attn_tiles(ch.trip_slot, ids_d.shape[1]))
+                                           attn_tiles=build_attn_tiles(ch.trip_slot, ids_d.shape[1]),
+                                           attn_tiles_cls=build_attn_tiles(ch.trip_slot, 1))
             out.index_copy_(0, torch.from_numpy(ch.flat_pos).to(self.device), s)
         return out.view(Q, K)
 

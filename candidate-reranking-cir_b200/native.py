@@ -81,6 +81,7 @@ _SIGS = {
     "cir_set_stream": (C.c_int, [vp, vp]),
     "cir_set_gemm_impl": (C.c_int, [vp, C.c_int]),
     "cir_set_attention_impl": (C.c_int, [vp, C.c_int]),
+    "cir_set_prune_last_layer": (C.c_int, [vp, C.c_int]),
     "cir_get_dtype": (C.c_int, [vp]),
     "cir_launch_count": (i64, [vp, C.c_int]),
     "cir_profile_gemm": (C.c_int, [vp, C.c_int]),
@@ -106,7 +107,7 @@ _SIGS = {
     "cir_stage1_encode": (C.c_int, [vp, C.POINTER(Stage1Weights), vp, vp, vp, vp, i64, i64, i64, vp, vp, C.c_int, vp, C.c_size_t]),
     "cir_stage1_gallery_embed": (C.c_int, [vp, C.POINTER(Stage1Weights), vp, i64, i64, vp, vp, C.c_size_t]),
     "cir_stage2_workspace_bytes": (C.c_size_t, [vp, i64, i64, i64, i64, i64]),
-    "cir_stage2_score": (C.c_int, [vp, C.POINTER(Stage2Weights), vp, vp, i64, vp, vp, vp, i64, i64, i64, vp, vp, i64, vp, i64, vp, i64, vp, vp, vp, C.c_size_t]),
+    "cir_stage2_score": (C.c_int, [vp, C.POINTER(Stage2Weights), vp, vp, i64, vp, vp, vp, i64, i64, i64, vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, C.c_size_t]),
 }
 
 _lib = None

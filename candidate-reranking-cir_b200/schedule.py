@@ -110,8 +110,8 @@ def build_attn_work(trip_slot: np.ndarray, L: int, warps: int = 8) -> np.ndarray
 def build_attn_tiles(trip_slot: np.ndarray, L: int) -> np.ndarray:
     """Tile list for the tcgen05 attention kernel (``cir_attn_args.tiles``): int32 [W,4] =
     (first triplet, triplets in the tile, first query row, rows per triplet RB).  A tile is 128 query
-    rows: 128/RB consecutive triplets of ONE candidate run (RB = 32 or 64), or a 128-row slice of a
-    single triplet when L > 64."""
+    rows: 128/RB consecutive triplets of ONE candidate run (RB = L rounded up to a power of two), or a
+    128-row slice of a single triplet when L > 64."""
     trip_slot = np.asarray(trip_slot)
     if trip_slot.size == 0:
         return np.zeros((0, 4), np.int32)
@@ -125,7 +125,9 @@ def build_attn_tiles(trip_slot: np.ndarray, L: int) -> np.ndarray:
         out[:, 2] = np.tile(np.arange(nslices) * 128, trip_slot.size)
         out[:, 3] = 128
         return out
-    RB = 32 if L <= 32 else 64
+    RB = 1
+    while RB < L:
+        RB *= 2                      # rows per triplet padded to a power of two (divides 128)
     G = 128 // RB
     starts = np.flatnonzero(np.r_[True, trip_slot[1:] != trip_slot[:-1]])
     counts = np.diff(np.r_[starts, trip_slot.size])

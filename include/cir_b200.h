@@ -66,6 +66,8 @@ int  cir_destroy(cir_ctx* ctx);
 int  cir_set_stream(cir_ctx* ctx, void* cuda_stream);       /* cudaStream_t */
 int  cir_set_gemm_impl(cir_ctx* ctx, int impl);              /* CIR_GEMM_* */
 int  cir_set_attention_impl(cir_ctx* ctx, int impl);      /* 0 auto (tcgen05 where eligible, else mma.sync), 1 CUDA-core kernel, 2 mma.sync only */
+/* stage II: compute layer 11 only for the two CLS query rows that the encoder returns (default on; 0 = all rows) */
+int  cir_set_prune_last_layer(cir_ctx* ctx, int enable);
 int  cir_get_dtype(const cir_ctx* ctx);
 /* number of kernel launches issued through this context since the last reset (bench.py's gpu_launches) */
 int64_t cir_launch_count(cir_ctx* ctx, int reset);
@@ -261,7 +263,7 @@ typedef struct cir_stage2_weights {
  *   trip_query int32 [T] -> row of z_t/ids/mask; trip_slot int32 [T] -> position in cand_list
  *   attn_work int32 [W,4] / attn_tiles int32 [W',4] optional cross-attention work lists (see
  *   cir_attn_args.work / .tiles; both require trip_slot sorted so that triplets naming the same candidate
- *   are adjacent)
+ *   are adjacent); attn_tiles_cls: the tile list for one query row per triplet (last layer, CLS only)
  *   scores fp32 [T] (class-0 logit); feats fp32 [T,1536] optional (cat(CLS0,CLS1), nlvr_encoder.py:909) */
 size_t cir_stage2_workspace_bytes(const cir_ctx* ctx, int64_t T, int64_t C, int64_t Q, int64_t L, int64_t N);
 int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const void* gallery_tokens,
@@ -270,6 +272,7 @@ int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const void* gall
                      const int32_t* trip_query, const int32_t* trip_slot, int64_t T,
                      const int32_t* attn_work, int64_t num_attn_work,
                      const int32_t* attn_tiles, int64_t num_attn_tiles,
+                     const int32_t* attn_tiles_cls, int64_t num_attn_tiles_cls,
                      float* scores, float* feats, void* workspace, size_t workspace_bytes);
 
 #ifdef __cplusplus

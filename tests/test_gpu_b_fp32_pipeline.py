@@ -74,7 +74,7 @@ def test_batched_candidate_major_matches_reference(small):
         m2.engine.max_triplets, m2.engine.max_candidates = mt, mc
         s = m2.score_triplets(z_t, ids, mask, tokens2, g["cand_idx"])
         assert np.abs(s.cpu().numpy() - g["scores"]).max() < 1e-4
-    m2.engine.max_triplets, m2.engine.max_candidates = 2048, 48
+    m2.engine.max_triplets, m2.engine.max_candidates = 4096, 64
     # features (cat of the two CLS vectors) are a stronger check than the 2-way head
     ch = cir.schedule.plan_chunks(g["cand_idx"])[0]
     eng = m2.engine
@@ -121,3 +121,19 @@ def test_L32_reference_init(small):
     tokens2 = m2.img_embed(syn.make_images(int(g["G"]), 384, seed=1))
     s = m2.score_triplets(torch.tensor(g["z_t"]).cuda(), torch.tensor(g["ids"]), torch.tensor(g["mask"]), tokens2, g["cand_idx"])
     assert np.abs(s.cpu().numpy() - g["scores"]).max() < 1e-4
+
+
+def test_last_layer_pruning_is_exact(small):
+    """Computing layer 11 for the CLS rows only must not change the scores (fp32: same arithmetic per row)."""
+    g, m1, m2, images, tokens2 = small
+    ids, mask = torch.tensor(g["ids"]), torch.tensor(g["mask"])
+    z_t = torch.tensor(g["z_t"]).cuda()
+    eng = m2.engine
+    a = m2.score_triplets(z_t, ids, mask, tokens2, g["cand_idx"])
+    eng.set_prune_last_layer(False)
+    try:
+        b = m2.score_triplets(z_t, ids, mask, tokens2, g["cand_idx"])
+    finally:
+        eng.set_prune_last_layer(True)
+    assert (a - b).abs().max() < 2e-6
+    assert np.abs(b.cpu().numpy() - g["scores"]).max() < 1e-4

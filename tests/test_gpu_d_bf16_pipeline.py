@@ -96,3 +96,18 @@ def test_validate_drivers_on_synthetic_dataset(small):
     assert got == want
     r10, r50 = V2.compute_fiq_val_metrics(ds, m2, m1, tokens2, names)
     assert (r10, r50) == O.fiq_metrics(logits.cpu(), ds.K_labels)
+
+
+def test_last_layer_pruning_bf16(small):
+    g, m1, m2, images, tokens2 = small
+    ids, mask = torch.tensor(g["ids"]), torch.tensor(g["mask"])
+    z_t = torch.tensor(g["z_t"]).cuda().bfloat16()
+    eng = m2.engine
+    a = m2.score_triplets(z_t, ids, mask, tokens2, g["cand_idx"])
+    eng.set_prune_last_layer(False)
+    try:
+        b = m2.score_triplets(z_t, ids, mask, tokens2, g["cand_idx"])
+    finally:
+        eng.set_prune_last_layer(True)
+    assert (a - b).abs().max() < 5e-3          # different tile shapes / kernels on the last layer, same math
+    assert np.abs(a.cpu().numpy() - g["scores"]).max() <= SCORE_TOL

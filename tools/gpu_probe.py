@@ -63,4 +63,4 @@ if __name__ == "__main__":
     if "stage2" in which:
         stage2_probe()
     if "stage2_profile" in which:      # one short pass for an ncu launch list
-        stage2_probe(reps=1, configs=((2048, 48),), Q=96)
+        stage2_probe(reps=1, configs=((4096, 64),), Q=96)
