@@ -2,18 +2,20 @@
 // dual-stream encoder (32 text rows x 577 image keys per (triplet, stream, head),
 // src/nlvr_encoder.py:175-217) and the ViT self-attention (src/vit.py:74-82).
 //
-// One CTA = one 128-row query tile of one head.  A tile is (128/RB) batches x RB rows that all attend
-// the SAME K/V batch (candidate-major triplets: 4 triplets x 32 rows share one candidate image), so the
-// 128-row UMMA shape is filled even though a single triplet has only 32 query rows.
+// One CTA = one 128-row query tile of one head; two CTAs are resident per SM.  A tile is (128/RB) batches
+// x RB rows that all attend the SAME K/V batch (candidate-major triplets: 4 triplets x 32 rows share one
+// candidate image), so the 128-row UMMA shape is filled although a triplet has only 32 query rows.
 //
-//   warps 0-3 (128 threads)  softmax: thread r owns query row r == TMEM lane r.  Per 128-key chunk:
-//                            tcgen05.ld S -> row max -> exp2 -> bf16 P written to 128B-swizzled shared
-//                            memory (the A operand of the PV product) -> O_j merged into registers.
-//   warp 4                   one elected thread: TMA loads of K/V chunks (2-deep rings) and all
-//                            tcgen05.mma issue:  S_j = Q K_j^T  (A=Q smem, B=K_j smem, both K-major)
-//                                                O_j = P_j V_j  (A=P smem K-major, B=V_j smem MN-major)
-//   TMEM: S 128 columns + O 64 columns (256 allocated) -> two CTAs per SM overlap each other's
-//   MMA / softmax phases.  Scores and probabilities never touch HBM.
+//   warps 0-3   softmax: thread r owns query row r == TMEM lane r.  Per 64-key chunk ONE tcgen05.ld sweep
+//               brings the row's scores into registers, row max -> exp2 -> bf16 P written to a 128B-swizzled
+//               shared-memory atom (the A operand of the PV product).  S and P are double-buffered, so the
+//               tensor core computes S_{j+1}, S_{j+2} while the softmax works on chunk j.  O accumulates in
+//               TMEM across chunks; the reference max moves lazily (only when the row max grew by more than
+//               2^8), so the O rescale (tcgen05.ld / tcgen05.st) is a rare path.
+//   warp 4      one elected thread: TMA loads of K/V chunks (3-deep rings) and all tcgen05.mma issue:
+//                 S_j = Q K_j^T  (A=Q smem, B=K_j smem, both K-major)
+//                 O  += P_j V_j  (A=P smem K-major, B=V_j smem MN-major)
+//   TMEM: S0, S1 (64 columns each) + O (64).  Scores and probabilities never touch HBM.
 #include "common.cuh"
 #include "tcgen05_ptx.cuh"
 
@@ -21,16 +23,17 @@ namespace fatc {
 
 using namespace tc;
 
-constexpr int KC = 128;                 // keys per chunk
-constexpr int THREADS = 160;
+constexpr int KC = 64;                  // keys per chunk (one 128-byte swizzle atom of P per chunk)
+constexpr int KS = 3;                   // K / V ring depth
+constexpr int THREADS = 160;            // 4 softmax warps + 1 control warp
 constexpr int Q_BYTES = 128 * 128;      // 128 rows x 64 bf16
-constexpr int KV_BYTES = KC * 128;      // 128 keys x 64 bf16
-constexpr int P_BYTES = 2 * 128 * 128;  // two 64-key atoms of [128 rows x 128 B]
-constexpr int OFF_Q = 0, OFF_K = Q_BYTES, OFF_V = OFF_K + 2 * KV_BYTES, OFF_P = OFF_V + 2 * KV_BYTES;
-constexpr int OFF_BAR = OFF_P + P_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int KV_BYTES = KC * 128;      // 64 keys x 64 bf16
+constexpr int P_BYTES = 128 * 128;      // [128 rows x 64 keys] bf16
+constexpr int OFF_Q = 0, OFF_K = Q_BYTES, OFF_V = OFF_K + KS * KV_BYTES, OFF_P = OFF_V + KS * KV_BYTES;
+constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
 constexpr int TMEM_COLS = 256;
-constexpr int S_COL = 0, O_COL = 128;
+constexpr int S_COL = 0, O_COL = 128;   // S buffers at 0 and 64, O at 128
 
 // instruction descriptor with an MN-major B operand (V is [key][dh], dh contiguous): bit 16
 __host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int m, int n) { return make_idesc_bf16(m, n) | (1u << 16); }
@@ -47,40 +50,59 @@ __device__ __forceinline__ float ex2_approx(float x) {       // one MUFU.EX2; ex
   return r;
 }
 
+// O[row, 0:64] *= alpha in TMEM (whole warp, each lane its own row/alpha); rare path, kept out of line
+__device__ __noinline__ void rescale_o(uint32_t o_addr, float alpha) {
+#pragma unroll
+  for (int hh = 0; hh < 2; hh++) {
+    uint32_t ov[32];
+    __syncwarp();
+    tmem_ld_32x32b_x32(o_addr + hh * 32, ov);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i++) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+    tmem_st_32x32b_x32(o_addr + hh * 32, ov);
+  }
+  tmem_st_wait();
+}
+
 __global__ void __launch_bounds__(THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, const cir_attn_args p,
-                    int tiles_per_batch) {
+                    int ctas_per_batch) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.y;
-  // ---- tile descriptor
+  // ---- CTA descriptor: 128 query rows r -> batch batch0 + r / RB, query row row0 + r % RB
   int batch0, nb, row0, RB;
   if (p.tiles) {
     const int4 t = reinterpret_cast<const int4*>(p.tiles)[blockIdx.x];
     batch0 = t.x; nb = t.y; row0 = t.z; RB = t.w;
   } else {
-    batch0 = blockIdx.x / tiles_per_batch; nb = 1; row0 = (blockIdx.x % tiles_per_batch) * 128; RB = 128;
+    batch0 = blockIdx.x / ctas_per_batch; nb = 1; row0 = (blockIdx.x % ctas_per_batch) * 128; RB = 128;
   }
   const int kvb = p.kv_index ? p.kv_index[batch0] : batch0;
   const int nch = (p.Lk + KC - 1) / KC;
 
-  // barriers: kfull[2], vfull[2], vfree[2], sfull, sfree, pfull, ofull, ofree, qfull, tmem_ptr
+  // barriers (all indexed by chunk parity so a waiter is never more than one phase behind):
+  //   kfull[KS] vfull[KS] | sfull[2] pfull[2] pvdone[2] | qfull | tmem_ptr
   const uint32_t bar = sbase + OFF_BAR;
-  auto kfull = [&](int b) { return bar + 8u * b; };
-  auto vfull = [&](int b) { return bar + 16u + 8u * b; };
-  auto vfree = [&](int b) { return bar + 32u + 8u * b; };
-  const uint32_t sfull = bar + 48, sfree = bar + 56, pfull = bar + 64, ofull = bar + 72, ofree = bar + 80, qfull = bar + 88;
-  const uint32_t tmem_ptr_smem = bar + 96;
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 96);
+  auto kfull = [&](int s) { return bar + 8u * s; };
+  auto vfull = [&](int s) { return bar + 8u * (KS + s); };
+  auto sfull = [&](int b) { return bar + 8u * (2 * KS + b); };
+  auto pfull = [&](int b) { return bar + 8u * (2 * KS + 2 + b); };
+  auto pvdone = [&](int b) { return bar + 8u * (2 * KS + 4 + b); };
+  const uint32_t qfull = bar + 8u * (2 * KS + 6);
+  const uint32_t tmem_ptr_smem = qfull + 8;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (2 * KS + 6) + 8);
 
   if ((sbase & 1023u) != 0) { if (tid == 0) printf("cir: attention_tc smem misaligned\n"); __trap(); }
   if (warp == 4) {
     if (elect_one()) {
       tma_prefetch_desc(&map_k);
       tma_prefetch_desc(&map_v);
-      for (int b = 0; b < 2; b++) { mbar_init(kfull(b), 1); mbar_init(vfull(b), 1); mbar_init(vfree(b), 1); }
-      mbar_init(sfull, 1); mbar_init(sfree, 4); mbar_init(pfull, 4); mbar_init(ofull, 1); mbar_init(ofree, 4); mbar_init(qfull, 4);
+      for (int s = 0; s < KS; s++) { mbar_init(kfull(s), 1); mbar_init(vfull(s), 1); }
+      for (int b = 0; b < 2; b++) { mbar_init(sfull(b), 1); mbar_init(pfull(b), 4); mbar_init(pvdone(b), 1); }
+      mbar_init(qfull, 4);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -96,59 +118,55 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_cons
     if (elect_one()) {
       const int32_t krow0 = kvb * p.Lk;
       const int32_t col = h * 64;
-      const int pre = nch < 2 ? nch : 2;
-      for (int j = 0; j < pre; j++) {
-        mbar_expect_tx(kfull(j), KV_BYTES);
-        tma_load_2d(sbase + OFF_K + j * KV_BYTES, &map_k, kfull(j), col, krow0 + j * KC);
-        mbar_expect_tx(vfull(j), KV_BYTES);
-        tma_load_2d(sbase + OFF_V + j * KV_BYTES, &map_v, vfull(j), col, krow0 + j * KC);
-      }
-      mbar_wait(qfull, 0);                                  // Q tile written (generic proxy) + proxy fence by the softmax warps
-      tcgen05_fence_after();
-      const uint64_t qdesc = make_smem_desc_sw128(sbase + OFF_Q);
-      for (int j = 0; j < nch; j++) {
-        const int b = j & 1;
-        const uint32_t par2 = (uint32_t)((j >> 1) & 1);
+      auto load_k = [&](int j) {
+        const int s = j % KS;
+        mbar_expect_tx(kfull(s), KV_BYTES);
+        tma_load_2d(sbase + OFF_K + s * KV_BYTES, &map_k, kfull(s), col, krow0 + j * KC);
+      };
+      auto load_v = [&](int j) {
+        const int s = j % KS;
+        mbar_expect_tx(vfull(s), KV_BYTES);
+        tma_load_2d(sbase + OFF_V + s * KV_BYTES, &map_v, vfull(s), col, krow0 + j * KC);
+      };
+      auto n_pad_of = [&](int j) {
         const int keys = (p.Lk - j * KC) < KC ? (p.Lk - j * KC) : KC;
-        const int n_pad = (keys + 15) & ~15;                // UMMA N (multiple of 16); padded keys are masked in the softmax
-        // ---- S_j = Q K_j^T
-        mbar_wait(kfull(b), par2);
-        if (j > 0) mbar_wait(sfree, (uint32_t)((j - 1) & 1));
+        return (keys + 15) & ~15;                            // UMMA N (multiple of 16); padded keys are masked in the softmax
+      };
+      const uint64_t qdesc = make_smem_desc_sw128(sbase + OFF_Q);
+      auto issue_s = [&](int j) {                           // S[j&1] = Q K_j^T
+        mbar_wait(kfull(j % KS), (uint32_t)((j / KS) & 1));
         tcgen05_fence_after();
-        {
-          const uint64_t kdesc = make_smem_desc_sw128(sbase + OFF_K + b * KV_BYTES);
-          const uint32_t idesc = make_idesc_bf16(128, n_pad);
+        const uint64_t kdesc = make_smem_desc_sw128(sbase + OFF_K + (j % KS) * KV_BYTES);
+        const uint32_t idesc = make_idesc_bf16(128, n_pad_of(j));
 #pragma unroll
-          for (int k = 0; k < 4; k++) umma_bf16(tmem_base + S_COL, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc, (uint32_t)(k != 0));
-          umma_commit(sfull);
-        }
-        // ---- V ring: chunk j+1 reuses the buffer of chunk j-1 once PV_{j-1} retired
-        if (j >= 1 && j + 1 < nch) {
-          const int bb = (j + 1) & 1;
-          mbar_wait(vfree(bb), (uint32_t)(((j - 1) >> 1) & 1));
-          mbar_expect_tx(vfull(bb), KV_BYTES);
-          tma_load_2d(sbase + OFF_V + bb * KV_BYTES, &map_v, vfull(bb), col, krow0 + (j + 1) * KC);
-        }
-        // ---- O_j = P_j V_j
-        mbar_wait(pfull, (uint32_t)(j & 1));                 // P_j in shared memory; S_j fully consumed (so K_j is free too)
-        if (j + 2 < nch) {                                   // K ring: two chunks ahead
-          mbar_expect_tx(kfull(b), KV_BYTES);
-          tma_load_2d(sbase + OFF_K + b * KV_BYTES, &map_k, kfull(b), col, krow0 + (j + 2) * KC);
-        }
-        mbar_wait(vfull(b), par2);
-        if (j > 0) mbar_wait(ofree, (uint32_t)((j - 1) & 1));
+        for (int k = 0; k < 4; k++)
+          umma_bf16(tmem_base + S_COL + (j & 1) * 64, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc, (uint32_t)(k != 0));
+        umma_commit(sfull(j & 1));
+      };
+      const int pre = nch < KS ? nch : KS;
+      for (int j = 0; j < pre; j++) { load_k(j); load_v(j); }
+      mbar_wait(qfull, 0);                                  // Q tile written (generic proxy) + proxy fence by the softmax warps
+      issue_s(0);
+      if (nch > 1) issue_s(1);
+      for (int j = 0; j < nch; j++) {
+        mbar_wait(pfull(j & 1), (uint32_t)((j >> 1) & 1));   // P_j in shared memory, S_j consumed, O rescaled if needed
+        mbar_wait(vfull(j % KS), (uint32_t)((j / KS) & 1));
         tcgen05_fence_after();
-        {
+        {                                                    // O (+)= P_j V_j, accumulating in TMEM across chunks
           const uint32_t idesc = make_idesc_bf16_bmn(128, 64);
-          const int ksteps = n_pad >> 4;
+          const int ksteps = n_pad_of(j) >> 4;
           for (int k = 0; k < ksteps; k++) {
-            // A: P atom (k/4) of [128 rows x 64 keys], +32 B per 16 keys inside the atom.  B: V rows 16k.. (16 x 128 B)
-            const uint64_t pdesc = make_smem_desc_sw128(sbase + OFF_P + (k >> 2) * (128 * 128)) + (uint64_t)((k & 3) * 2);
-            const uint64_t vdesc = make_smem_desc_sw128(sbase + OFF_V + b * KV_BYTES + k * 2048);
-            umma_bf16(tmem_base + O_COL, pdesc, vdesc, idesc, (uint32_t)(k != 0));
+            const uint64_t pdesc = make_smem_desc_sw128(sbase + OFF_P + (j & 1) * P_BYTES) + (uint64_t)(k * 2);    // +32 B per 16 keys
+            const uint64_t vdesc = make_smem_desc_sw128(sbase + OFF_V + (j % KS) * KV_BYTES + k * 2048);         // 16 key rows x 128 B
+            umma_bf16(tmem_base + O_COL, pdesc, vdesc, idesc, (uint32_t)((j | k) != 0));
           }
-          umma_commit(ofull);
-          umma_commit(vfree(b));
+          umma_commit(pvdone(j & 1));
+        }
+        if (j + 2 < nch) issue_s(j + 2);                     // S buffer j&1 was drained before pfull(j)
+        if (j + KS < nch) load_k(j + KS);                    // S_j retired long ago -> K_j's stage is free
+        if (j >= 1 && j - 1 + KS < nch) {                    // V_{j-1}'s stage once PV_{j-1} retired
+          mbar_wait(pvdone((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
+          load_v(j - 1 + KS);
         }
       }
     }
@@ -171,104 +189,89 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_cons
       if (lane == 0) mbar_arrive(qfull);
     }
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t o_addr = lane_addr + O_COL;
     const float sl2 = p.scale * 1.4426950408889634f;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; i++) o[i] = 0.f;
-    float m = -INFINITY, l = 0.f, a_pending = 0.f;
+    float m = -INFINITY, l = 0.f;                            // m: lazily updated reference max (scaled log2 domain)
     for (int j = 0; j < nch; j++) {
+      const int pb = j & 1;
       const int keys = (p.Lk - j * KC) < KC ? (p.Lk - j * KC) : KC;
-      const int n_pad = (keys + 15) & ~15;
-      const int npieces = (n_pad + 31) >> 5;
-      mbar_wait(sfull, (uint32_t)(j & 1));
-      tcgen05_fence_after();
-      // ---- pass 1: row max over the valid keys of this chunk (3-input FMNMX3; full chunks need no key test)
-      float cmax = -INFINITY;
       const bool full_chunk = keys == KC;
-      for (int pc = 0; pc < npieces; pc++) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_32x32b_x32(lane_addr + S_COL + pc * 32, v);
-        tmem_ld_wait();
-        if (full_chunk) {
+      const bool two = keys > 32;                            // second 32-column piece needed?
+      mbar_wait(sfull(pb), (uint32_t)((j >> 1) & 1));
+      tcgen05_fence_after();
+      // ---- the row's 64 scores -> registers in one sweep
+      uint32_t v0[32], v1[32];
+      __syncwarp();
+      tmem_ld_32x32b_x32(lane_addr + S_COL + pb * 64, v0);
+      if (two) tmem_ld_32x32b_x32(lane_addr + S_COL + pb * 64 + 32, v1);
+      tmem_ld_wait();
+      // ---- row max of the chunk
+      float cmax = -INFINITY;
+      if (full_chunk) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) cmax = max3(cmax, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-        } else {
+        for (int i = 0; i < 32; i += 2) cmax = max3(cmax, __uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
 #pragma unroll
-          for (int i = 0; i < 32; i++) if (pc * 32 + i < keys) cmax = fmaxf(cmax, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; i += 2) cmax = max3(cmax, __uint_as_float(v1[i]), __uint_as_float(v1[i + 1]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i++) if (i < keys) cmax = fmaxf(cmax, __uint_as_float(v0[i]));
+        if (two) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) if (32 + i < keys) cmax = fmaxf(cmax, __uint_as_float(v1[i]));
         }
       }
-      const float m_new = fmaxf(m, cmax * sl2);              // scale > 0: max commutes with the scaling
-      const float alpha = ex2_approx(m - m_new);             // first chunk: exp2(-inf) = 0
-      // ---- merge O_{j-1} (computed against the previous max) while the tensor core is idle anyway
-      if (j > 0) {
-        mbar_wait(ofull, (uint32_t)((j - 1) & 1));
+      cmax *= sl2;                                           // scale > 0: max commutes with the scaling
+      // ---- lazy reference max: move it only when the row max grew by more than 2^8; the (rare) move rescales
+      //      l and the O accumulator in TMEM.  Otherwise exp2(s - m) <= 256: harmless in fp32 / bf16.
+      const bool grow = cmax > m + 8.0f;
+      if (j == 0) {
+        m = cmax;
+      } else if (__any_sync(0xffffffffu, grow)) {
+        mbar_wait(pvdone((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));      // every PV issued so far has retired
         tcgen05_fence_after();
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-          uint32_t v[32];
-          __syncwarp();
-          tmem_ld_32x32b_x32(lane_addr + O_COL + hh * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i++) o[hh * 32 + i] = fmaf(o[hh * 32 + i], a_pending, __uint_as_float(v[i]));
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ofree);
+        const float m_new = grow ? cmax : m;
+        const float alpha = ex2_approx(m - m_new);           // 1 for rows that keep their reference
+        l *= alpha;
+        m = m_new;
+        rescale_o(o_addr, alpha);
       }
-      a_pending = alpha;
-      l *= alpha;
-      m = m_new;
-      // ---- pass 2: P = exp2(S*c - m) as bf16 into the swizzled A-operand tile; padded keys -> 0
-      for (int pc = 0; pc < npieces; pc++) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_32x32b_x32(lane_addr + S_COL + pc * 32, v);
-        tmem_ld_wait();
-        float pr[32];
-        if (full_chunk) {
+      if (j >= 2) mbar_wait(pvdone(pb), (uint32_t)(((j - 2) >> 1) & 1));     // P buffer pb: PV_{j-2} has read it
+      // ---- P = exp2(S*c - m) as bf16 into the swizzled A-operand tile (one 128 B row per thread); padded keys -> 0
+      uint8_t* prow = smem + OFF_P + pb * P_BYTES + r * 128;
 #pragma unroll
-          for (int i = 0; i < 32; i++) pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m));
-        } else {
+      for (int c = 0; c < 8; c++) {
+        float e[8];
 #pragma unroll
-          for (int i = 0; i < 32; i++) {
-            const float e = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m));
-            pr[i] = (pc * 32 + i < keys) ? e : 0.f;
-          }
+        for (int q = 0; q < 8; q++) {
+          const int i = c * 8 + q;
+          const float sv = __uint_as_float(i < 32 ? v0[i & 31] : v1[i & 31]);
+          e[q] = ex2_approx(fmaf(sv, sl2, -m));
+          if (!full_chunk && i >= keys) e[q] = 0.f;
         }
-        float ls = 0.f;
+        l += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+        uint4 w;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w);
 #pragma unroll
-        for (int i = 0; i < 32; i++) ls += pr[i];
-        l += ls;
-        // keys pc*32 .. pc*32+31 -> atom (pc >> 1), 16 B pieces ((pc & 1) * 4 + 0..3) of row r
-        uint8_t* prow = smem + OFF_P + (pc >> 1) * (128 * 128) + r * 128;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          uint4 w;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-          for (int q = 0; q < 4; q++) h2[q] = __floats2bfloat162_rn(pr[c * 8 + 2 * q], pr[c * 8 + 2 * q + 1]);
-          const int piece = (pc & 1) * 4 + c;
-          *reinterpret_cast<uint4*>(prow + ((piece ^ (r & 7)) << 4)) = w;
-        }
+        for (int q = 0; q < 4; q++) h2[q] = __floats2bfloat162_rn(e[2 * q], e[2 * q + 1]);
+        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = w;
       }
       fence_proxy_async();                                   // generic-proxy P writes -> visible to the tensor core (async proxy)
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(pfull); mbar_arrive(sfree); }
+      if (lane == 0) mbar_arrive(pfull(pb));
     }
-    // ---- last O_j, normalise, store
-    mbar_wait(ofull, (uint32_t)((nch - 1) & 1));
+    // ---- O, normalise, store
+    mbar_wait(pvdone((nch - 1) & 1), (uint32_t)(((nch - 1) >> 1) & 1));
     tcgen05_fence_after();
+    float o[64];
 #pragma unroll
     for (int hh = 0; hh < 2; hh++) {
-      uint32_t v[32];
+      uint32_t ov[32];
       __syncwarp();
-      tmem_ld_32x32b_x32(lane_addr + O_COL + hh * 32, v);
+      tmem_ld_32x32b_x32(o_addr + hh * 32, ov);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; i++) o[hh * 32 + i] = fmaf(o[hh * 32 + i], a_pending, __uint_as_float(v[i]));
+      for (int i = 0; i < 32; i++) o[hh * 32 + i] = __uint_as_float(ov[i]);
     }
     if (valid) {
       const float inv = 1.0f / l;
@@ -300,7 +303,7 @@ int cir_attention_tc(cir_ctx* ctx, const cir_attn_args* a) {
       ((uintptr_t)a->k & 15) || ((uintptr_t)a->v & 15) || ((uintptr_t)a->q & 15) || ((uintptr_t)a->o & 15) ||
       (a->q_rs % 8) || (a->q_bs % 8) || (a->o_rs % 8) || (a->o_bs % 8))
     return CIR_EUNSUPPORTED;
-  if (!a->tiles && a->Lq <= 64 && a->B > 1) return CIR_EUNSUPPORTED;      // unshared short queries would waste 1/2..3/4 of every tile
+  if (!a->tiles && a->Lq <= 64 && a->B > 1) return CIR_EUNSUPPORTED;      // unshared short queries would waste most of every tile
   const int64_t kv_rows = (int64_t)a->kv_batches * a->Lk;
   if (kv_rows >= (1ll << 31)) return CIR_EUNSUPPORTED;
   CUtensorMap mk, mv;
@@ -311,10 +314,10 @@ int cir_attention_tc(cir_ctx* ctx, const cir_attn_args* a) {
     CIR_CUDA(cudaFuncSetAttribute(fatc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fatc::SMEM_BYTES));
     attr_set = true;
   }
-  const int tpb = (a->Lq + 127) / 128;
-  const unsigned gx = a->tiles ? (unsigned)a->num_tiles : (unsigned)(a->B * tpb);
+  const int cpb = (a->Lq + 127) / 128;
+  const unsigned gx = a->tiles ? (unsigned)a->num_tiles : (unsigned)(a->B * cpb);
   if (gx == 0) return CIR_OK;
-  fatc::attention_tc_kernel<<<dim3(gx, (unsigned)a->H), fatc::THREADS, fatc::SMEM_BYTES, ctx->stream>>>(mk, mv, *a, tpb);
+  fatc::attention_tc_kernel<<<dim3(gx, (unsigned)a->H), fatc::THREADS, fatc::SMEM_BYTES, ctx->stream>>>(mk, mv, *a, cpb);
   CIR_LAUNCH_CHECK(ctx);
   return CIR_OK;
 }

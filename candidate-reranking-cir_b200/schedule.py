@@ -110,13 +110,13 @@ def build_attn_work(trip_slot: np.ndarray, L: int, warps: int = 8) -> np.ndarray
 def build_attn_tiles(trip_slot: np.ndarray, L: int) -> np.ndarray:
     """Tile list for the tcgen05 attention kernel (``cir_attn_args.tiles``): int32 [W,4] =
     (first triplet, triplets in the tile, first query row, rows per triplet RB).  A tile is 128 query
-    rows: 128/RB consecutive triplets of ONE candidate run (RB = L rounded up to a power of two), or a
-    128-row slice of a single triplet when L > 64."""
+    rows: 128/RB consecutive triplets of ONE candidate run, with RB = L rounded up to a power of two, or
+    a 128-row slice of a single triplet when L > 128."""
     trip_slot = np.asarray(trip_slot)
     if trip_slot.size == 0:
         return np.zeros((0, 4), np.int32)
     assert np.all(np.diff(trip_slot) >= 0), "trip_slot must be candidate-major (sorted)"
-    if L > 64:
+    if L > 128:
         nslices = (L + 127) // 128
         t = np.repeat(np.arange(trip_slot.size), nslices)
         out = np.zeros((t.size, 4), np.int32)

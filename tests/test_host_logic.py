@@ -123,7 +123,7 @@ def test_build_attn_tiles_cover():
     from importlib import import_module
     sched = import_module("candidate-reranking-cir_b200.schedule")
     slot = np.array([0, 0, 0, 0, 0, 1, 3, 3, 3, 3, 3, 3, 3, 3, 3], np.int32)
-    for L in (12, 32, 40, 64, 100, 300):
+    for L in (1, 12, 32, 40, 64, 100, 300, 577):
         tiles = sched.build_attn_tiles(slot, L)
         rows = set()
         for b0, nb, row0, RB in tiles.tolist():

@@ -56,11 +56,49 @@ def stage2_probe(T_per=2048, C=48, L=32, reps=3, configs=((1024, 32), (2048, 48)
         print(f"stage2 Q={Q} K={K} L={L} G={G} chunk(T<={mt},C<={mc}): {ms:.1f} ms -> {Q*K/ms*1e3:.0f} triplets/s, {nl:.0f} launches/pass", flush=True)
 
 
+def attn_probe():
+    """cross-attention shape of one stage-II chunk: T triplets x 32 rows vs 577 keys, candidate runs of ~91"""
+    T, L, Lk, C = 4096, 32, 577, 45
+    slot = torch.sort(torch.arange(T) % C).values.int()
+    q = torch.randn(T, L, 768, device="cuda").bfloat16()
+    kv = torch.randn(C, Lk, 3072, device="cuda").bfloat16()
+    o = torch.empty(T, L, 1536, device="cuda", dtype=torch.bfloat16)
+    import ctypes as C_
+    sched = cir.schedule
+    tiles = e._i32(sched.build_attn_tiles(slot.numpy(), L))
+    work = e._i32(sched.build_attn_work(slot.numpy(), L))
+    slot_d = slot.cuda()
+    flops = 4.0 * T * L * Lk * 64 * 12
+
+    def call(impl, use_tiles):
+        a = N_.AttnArgs()
+        a.q, a.k, a.v, a.o = N_.ptr(q), N_.ptr(kv), N_.vp(kv.data_ptr() + 768 * 2), N_.ptr(o)
+        a.q_bs, a.q_rs = L * 768, 768
+        a.k_bs = a.v_bs = Lk * 3072
+        a.k_rs = a.v_rs = 3072
+        a.o_bs, a.o_rs = L * 1536, 1536
+        a.kv_index = N_.ptr(slot_d)
+        a.key_mask = a.mask_index = N_.vp(0)
+        a.work, a.num_work = (N_.ptr(work), work.shape[0]) if not use_tiles else (N_.vp(0), 0)
+        a.tiles, a.num_tiles = (N_.ptr(tiles), tiles.shape[0]) if use_tiles else (N_.vp(0), 0)
+        a.kv_batches = C
+        a.B, a.H, a.Lq, a.Lk, a.scale = T, 12, L, Lk, 0.125
+        e.set_attention_impl(impl)
+        e._sync_stream()
+        N_.check(e._lib.cir_attention(e.ctx, C_.byref(a)))
+        e.set_attention_impl(0)
+    for name, impl, ut in (("tcgen05", 0, True), ("mma.sync", 2, False)):
+        ms = timeit(lambda: call(impl, ut), warm=2, it=10)
+        print(f"cross-attn T={T} L={L} Lk={Lk} runs of ~{T//C}: {name}: {ms:.3f} ms  {flops/ms/1e9:.0f} TF/s (algorithmic)", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "stage2"]
     if "gemm" in which:
         gemm_probe()
     if "stage2" in which:
         stage2_probe()
+    if "attn" in which:
+        attn_probe()
     if "stage2_profile" in which:      # one short pass for an ncu launch list
         stage2_probe(reps=1, configs=((4096, 64),), Q=96)
