@@ -84,7 +84,6 @@ def blip_stage1(pretrained="", **kwargs):
     """src/blip_stage1.py:95-101; checkpoint key 'BLIP_Retrieval' (src/validate_stage2.py:347-348)."""
     model = BLIP_Retrieval(**kwargs)
     if pretrained:
-        ckpt = torch.load(pretrained, map_location="cpu")
-        sd = ckpt.get("BLIP_Retrieval", ckpt.get("model", ckpt))
-        model.load_state_dict(sd)
+        from .checkpoint import load_state_dict
+        model.load_state_dict(load_state_dict(pretrained, "BLIP_Retrieval", kwargs.get("image_size", model.image_size)))
     return model

@@ -96,7 +96,6 @@ def blip_stage2(pretrained="", **kwargs):
     {'BLIP_NLVR': state_dict} (src/validate_stage2.py:359-360) or {'model': state_dict}."""
     model = BLIP_NLVR(**kwargs)
     if pretrained:
-        ckpt = torch.load(pretrained, map_location="cpu")
-        sd = ckpt.get("BLIP_NLVR", ckpt.get("model", ckpt))
-        model.load_state_dict(sd)
+        from .checkpoint import load_state_dict
+        model.load_state_dict(load_state_dict(pretrained, "BLIP_NLVR", kwargs.get("image_size", model.image_size)))
     return model

@@ -56,6 +56,18 @@ def stage2_probe(T_per=2048, C=48, L=32, reps=3, configs=((1024, 32), (2048, 48)
         print(f"stage2 Q={Q} K={K} L={L} G={G} chunk(T<={mt},C<={mc}): {ms:.1f} ms -> {Q*K/ms*1e3:.0f} triplets/s, {nl:.0f} launches/pass", flush=True)
 
 
+def stage1_probe():
+    """stage-I candidate filtering: fused 1 - q @ G^T + per-query top-K (validate.py:57-58,202-210)"""
+    e32 = e
+    for (Q, G, K) in ((4181, 2297, 100), (4181, 100000, 100), (4181, 1000000, 200)):
+        g = torch.Generator().manual_seed(0)
+        q = torch.nn.functional.normalize(torch.randn(Q, 256, generator=g), dim=-1).cuda()
+        gal = torch.nn.functional.normalize(torch.randn(G, 256, device="cuda"), dim=-1)
+        excl = torch.randint(0, G, (Q,), generator=g)
+        ms = timeit(lambda: e32.stage1_topk(q, gal, K, exclude=excl), warm=1, it=3)
+        print(f"stage1 top-{K}: Q={Q} G={G}: {ms:.1f} ms -> {Q/ms*1e3:.0f} queries/s ({2.0*Q*G*256/ms/1e9:.1f} TF/s fp32 sims)", flush=True)
+
+
 def attn_probe():
     """cross-attention shape of one stage-II chunk: T triplets x 32 rows vs 577 keys, candidate runs of ~91"""
     T, L, Lk, C = 4096, 32, 577, 45
@@ -98,6 +110,8 @@ if __name__ == "__main__":
         gemm_probe()
     if "stage2" in which:
         stage2_probe()
+    if "stage1" in which:
+        stage1_probe()
     if "attn" in which:
         attn_probe()
     if "stage2_profile" in which:      # one short pass for an ncu launch list
