@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .blip import tokenize
-from .validate_stage2 import _fiq_captions, _name_index, _percent, _tokens
+from .validate_stage2 import LENGTH_BUCKET, _fiq_captions, _length_buckets, _name_index, _percent, _tokens
 
 
 def extract_index_features(images: torch.Tensor, index_names: List[str], blip_model, blip_stage2=False, blip_stage1=False,
@@ -37,7 +37,12 @@ def retrieve_topk(blip_model, dataset, index_features, index_features_normed_poo
     caps = list(dataset.captions) if cirr else _fiq_captions(dataset.captions)
     ids, mask = _tokens(blip_model, dataset, caps)
     gallery = eng.to_act(index_features)
-    _, q_emb = blip_model.encode_queries(gallery, ref_idx, ids, mask, want_z=False, want_emb=True, normalize_twice=cirr)
+    q_emb = torch.empty(len(ref_idx), 256, dtype=torch.float32, device=eng.device)
+    for rows, L in _length_buckets(mask, LENGTH_BUCKET):                            # each query at (about) its own length
+        r_t = torch.from_numpy(rows).to(eng.device)
+        _, qe = blip_model.encode_queries(gallery, ref_idx[rows], ids[r_t, :L].contiguous(), mask[r_t, :L].contiguous(),
+                                          want_z=False, want_emb=True, normalize_twice=cirr)
+        q_emb[r_t] = qe
     g_emb = index_features_normed_pooled.float()                                    # "already normed" (:55,:199)
     return eng.stage1_topk(q_emb, g_emb, k, exclude=ref_idx if cirr else None)
 
@@ -53,7 +58,7 @@ def compute_fiq_val_metrics(relative_val_dataset, blip_model, index_features, in
                             k: int = 100) -> Tuple[float, float, Dict]:
     """src/validate.py:33-99 -> (recall@10, recall@50, topk dict shaped like the saved file :87-94)."""
     eng = blip_model.engine
-    k = max(k, 50)
+    k = min(max(k, 50), len(index_names))
     top_dist, top_idx = retrieve_topk(blip_model, relative_val_dataset, index_features, index_features_normed_pooled, index_names, k, cirr=False)
     n2i = _name_index(index_names)
     tgt = np.array([n2i[n] for n in relative_val_dataset.target_names])
@@ -70,7 +75,7 @@ def compute_cirr_val_metrics(relative_val_dataset, blip_model, index_features, i
     (The subset/group recalls of the stage-I driver need the full ranking of the 5 group members; they
     are produced by the stage-II driver, src/validate_stage2.py:186-203.)"""
     eng = blip_model.engine
-    k = max(k, 50)
+    k = min(max(k, 50), len(index_names) - 1)          # the reference image is removed from every row (:207-210)
     top_dist, top_idx = retrieve_topk(blip_model, relative_val_dataset, index_features, index_features_normed_pooled, index_names, k, cirr=True)
     n2i = _name_index(index_names)
     tgt = np.array([n2i[n] for n in relative_val_dataset.target_names])

@@ -38,24 +38,54 @@ def _tokens(blip_model, dataset, captions):
     return tokenize(blip_model.tokenizer, tb if tb is not None else captions, blip_model.engine.device)
 
 
-def _predict(blip_model, model_stage1, dataset, index_names, index_features, captions, cand_names, row_active):
+LENGTH_BUCKET = 8      # queries are grouped by token length rounded up to a multiple of this
+
+
+def _length_buckets(mask: torch.Tensor, bucket: int):
+    """The reference tokenises one query at a time, so every query runs at its own length
+    (src/validate_stage2.py:104-106, padding='longest' over a batch of one).  Batching all queries at the
+    longest caption's length would waste FLOPs on padding, so queries are grouped by their own length
+    (rounded up to ``bucket``) and each group runs at that length; padded positions inside a group are
+    masked keys (-10000) exactly as in a padded reference batch.  Yields (row indices, L)."""
+    lens = mask.sum(dim=1).cpu().numpy()
+    Lmax = mask.shape[1]
+    padded = np.minimum(((np.maximum(lens, 1) + bucket - 1) // bucket) * bucket, Lmax)
+    for L in np.unique(padded):
+        yield np.flatnonzero(padded == L), int(L)
+
+
+def _predict(blip_model, model_stage1, dataset, index_names, index_features, captions, cand_names, row_active,
+             extra_cand_names=None):
+    """-> (scores [Q,K], extra scores [Q,K'] | None).  z_t is computed once per query and shared by both lists."""
     eng = blip_model.engine
     n2i = _name_index(index_names)
     ref_idx = np.array([n2i[n] for n in dataset.reference_names], dtype=np.int32)
-    cand_idx = np.vectorize(n2i.__getitem__, otypes=[np.int32])(np.asarray(cand_names))
+    to_idx = np.vectorize(n2i.__getitem__, otypes=[np.int32])
+    cand_idx = to_idx(np.asarray(cand_names))
+    extra_idx = None if extra_cand_names is None else to_idx(np.asarray(extra_cand_names))
     ids, mask = _tokens(blip_model, dataset, captions)
     gallery = eng.to_act(index_features)
-    # z_t from the frozen stage-I encoder on the reference image's tokens (src/validate_stage2.py:105-106,243-244)
-    z_t, _ = model_stage1.encode_queries(gallery, ref_idx, ids, mask, want_z=True, want_emb=False)
-    return blip_model.score_triplets(z_t, ids, mask, gallery, cand_idx, row_active), z_t, ids, mask, gallery, n2i
+    Q = cand_idx.shape[0]
+    scores = torch.empty(Q, cand_idx.shape[1], dtype=torch.float32, device=eng.device)
+    extra = None if extra_idx is None else torch.empty(Q, extra_idx.shape[1], dtype=torch.float32, device=eng.device)
+    active = np.ones(Q, bool) if row_active is None else np.asarray(row_active, bool)
+    for rows, L in _length_buckets(mask, LENGTH_BUCKET):
+        r_t = torch.from_numpy(rows).to(eng.device)
+        ids_b, mask_b = ids[r_t, :L].contiguous(), mask[r_t, :L].contiguous()
+        # z_t from the frozen stage-I encoder on the reference image's tokens (src/validate_stage2.py:105-106,243-244)
+        z_t, _ = model_stage1.encode_queries(gallery, ref_idx[rows], ids_b, mask_b, want_z=True, want_emb=False)
+        scores[r_t] = blip_model.score_triplets(z_t, ids_b, mask_b, gallery, cand_idx[rows], active[rows])
+        if extra is not None:
+            extra[r_t] = blip_model.score_triplets(z_t, ids_b, mask_b, gallery, extra_idx[rows], None)
+    return scores, extra
 
 
 def generate_fiq_val_predictions(blip_model, model_stage1, relative_val_dataset, index_names, index_features):
     """src/validate_stage2.py:69-129 -> (predicted_logits [Q,K] fp32 on device, target_names)."""
     caps = _fiq_captions(relative_val_dataset.captions)
     active = np.asarray(relative_val_dataset.K_labels).any(axis=1)                  # `if True in K_labels` (:95)
-    logits, *_ = _predict(blip_model, model_stage1, relative_val_dataset, index_names, index_features, caps,
-                          relative_val_dataset.K_sorted_index_names, active)
+    logits, _ = _predict(blip_model, model_stage1, relative_val_dataset, index_names, index_features, caps,
+                         relative_val_dataset.K_sorted_index_names, active)
     return logits, list(relative_val_dataset.target_names)
 
 
@@ -75,15 +105,13 @@ def generate_cirr_val_predictions(blip_model, model_stage1, relative_val_dataset
     reference_names, target_names, group_members_noRef)."""
     ds = relative_val_dataset
     active = np.asarray(ds.K_labels).any(axis=1)                                    # `if True in K_labels` (:239)
-    logits, z_t, ids, mask, gallery, n2i = _predict(blip_model, model_stage1, ds, index_names, index_features,
-                                                     list(ds.captions), ds.K_sorted_index_names, active)
     # group members without the reference image, scored for EVERY query (:260-269)
     gm = np.asarray(ds.group_members)
     refs = np.asarray(ds.reference_names)
     group_noref = [[m for m in row if m != r] for row, r in zip(gm.tolist(), refs.tolist())]
     assert all(len(g) == 5 for g in group_noref)
-    gidx = np.vectorize(n2i.__getitem__, otypes=[np.int32])(np.asarray(group_noref))
-    group_logits = blip_model.score_triplets(z_t, ids, mask, gallery, gidx, None)
+    logits, group_logits = _predict(blip_model, model_stage1, ds, index_names, index_features, list(ds.captions),
+                                    ds.K_sorted_index_names, active, extra_cand_names=group_noref)
     return logits, group_logits, list(ds.reference_names), list(ds.target_names), group_noref
 
 

@@ -90,6 +90,10 @@ def test_validate_drivers_on_synthetic_dataset(small):
     assert logits.shape == (Q, K) and glogits.shape == (Q, 5)
     inactive = ~ds.K_labels.any(1)
     assert torch.all(logits[torch.from_numpy(inactive).cuda()] == -99999.99)
+    # length-bucketed driver == one padded batch (padding only adds masked keys)
+    z_all, _ = m1.encode_queries(tokens2, ref.int(), ids.clone().index_fill_(1, torch.tensor([0]), 30523), mask, want_z=True, want_emb=False)
+    direct = m2.score_triplets(z_all, ids.clone().index_fill_(1, torch.tensor([0]), 30523), mask, tokens2, cand.numpy(), ds.K_labels.any(1))
+    assert (direct - logits).abs().max() < 2e-3
     got = V2.compute_cirr_val_metrics(ds, m2, m1, tokens2, names)
     gt = np.array(gm) == np.array(tn)[:, None]
     want = O.cirr_metrics(logits.cpu(), ds.K_labels, glogits.cpu(), gt)
@@ -111,3 +115,28 @@ def test_last_layer_pruning_bf16(small):
         eng.set_prune_last_layer(True)
     assert (a - b).abs().max() < 5e-3          # different tile shapes / kernels on the last layer, same math
     assert np.abs(a.cpu().numpy() - g["scores"]).max() <= SCORE_TOL
+
+
+def test_stage1_driver_on_synthetic_dataset(small):
+    """validate.py-shaped run: stage-I top-K (reference excluded), labels and recalls vs the oracle on the
+    CUDA path's own embeddings."""
+    g, m1, m2, images, tokens2 = small
+    G = int(g["G"])
+    names = syn.index_names_for(G)
+    tokens1, g_emb = m1.img_embed(images, return_pool_and_normalized=True)
+    Q, K = 5, 4
+    ref, tgt, ids, mask = syn.make_queries(Q, G, 10, seed=9, min_len=6)
+    tb = syn.TokenBatch(input_ids=ids, attention_mask=mask)
+    ds = syn.SyntheticRelativeDataset(names, ref, tgt, ["x"] * Q, np.zeros((Q, K), int), kind="cirr", token_batch=tb)
+    V1 = cir.validate
+    td, ti = V1.retrieve_topk(m1, ds, tokens1, g_emb, names, K, cirr=True)
+    assert ti.shape == (Q, K)
+    for q in range(Q):
+        assert int(ref[q]) not in ti[q].tolist()
+    _, q_emb = m1.encode_queries(tokens1, ref.int(), ids.clone().index_fill_(1, torch.tensor([0]), 30523), mask,
+                                 want_z=False, want_emb=True, normalize_twice=True)
+    wd, wi = O.stage1_topk(q_emb.cpu(), g_emb.cpu(), ref, K)
+    assert (td.cpu() - wd).abs().max() < 2e-3
+    r1, r5, r10, r50, topk = V1.compute_cirr_val_metrics(ds, m1, tokens1, g_emb, names, k=K)
+    assert topk["sorted_index_names"].shape[0] == Q and topk["labels"].shape[0] == Q
+    assert 0.0 <= r1 <= r5 <= r10 <= r50 <= 100.0
