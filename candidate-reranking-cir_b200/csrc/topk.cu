@@ -97,28 +97,29 @@ topk_rows_kernel(TopkParams p) {
     if (tid == 0) s_any = 0;
     __syncthreads();
     const uint64_t thresh = sbest[p.K - 1];            // current K-th best (KEY_MAX while not full)
-    bool any = false;
+    // compact the keys that can still enter the top-K (usually a handful once the lists have warmed up)
     for (int i = tid; i < CH; i += THREADS) {
-      uint64_t key = KEY_MAX;
       const int64_t c = c0 + i;
       if (c < p.ncols) {
         float v = row[c];
         if (p.one_minus) v = 1.0f - v;
         const int64_t gi = irow ? (int64_t)irow[c] : p.col_base + c;
-        if (gi != excl) key = ((uint64_t)ordered_bits(v) << 32) | (uint32_t)gi;
+        const uint64_t key = ((uint64_t)ordered_bits(v) << 32) | (uint32_t)gi;
+        if (gi != excl && key < thresh) schunk[atomicAdd(&s_any, 1)] = key;
       }
-      schunk[i] = key;
-      any |= key < thresh;
     }
-    if (any) s_any = 1;
     __syncthreads();
-    const int any_blk = s_any;
+    const int n = s_any;
     __syncthreads();                                    // s_any is rewritten at the top of the next chunk
-    if (!any_blk) continue;                             // nothing in this chunk beats the K-th best
-    bitonic_sort(schunk, CH);
-    // K smallest of (best U chunk): min(best[i], chunk[Kp-1-i]) is bitonic
+    if (n == 0) continue;                               // nothing in this chunk beats the K-th best
+    int m = 32;
+    while (m < n) m <<= 1;                              // sort only the survivors (order of arrival is irrelevant: keys are unique)
+    for (int i = n + tid; i < m; i += THREADS) schunk[i] = KEY_MAX;
+    bitonic_sort(schunk, m);
+    // K smallest of (best U survivors): min(best[i], cand[Kp-1-i]) is bitonic
     for (int i = tid; i < p.Kp; i += THREADS) {
-      const uint64_t a = sbest[i], b = schunk[p.Kp - 1 - i];
+      const int j = p.Kp - 1 - i;
+      const uint64_t a = sbest[i], b = j < m ? schunk[j] : KEY_MAX;
       sbest[i] = a < b ? a : b;
     }
     bitonic_merge(sbest, p.Kp);

@@ -68,6 +68,17 @@ def stage1_probe():
         print(f"stage1 top-{K}: Q={Q} G={G}: {ms:.1f} ms -> {Q/ms*1e3:.0f} queries/s ({2.0*Q*G*256/ms/1e9:.1f} TF/s fp32 sims)", flush=True)
 
 
+def vit_probe():
+    """gallery token extraction: ViT-B/16 @384 (src/vit.py:180-194), 110.967 GF per image"""
+    syn = cir.synthetic
+    sd2 = syn.make_stage2_state_dict(0, 384, "reference")
+    m2 = cir.blip_stage2.blip_stage2(image_size=384, state_dict=sd2, precision="bf16")
+    for B in (64, 128):
+        img = torch.randn(B, 3, 384, 384, device="cuda")
+        ms = timeit(lambda: m2.engine.vit_forward(m2._vit, img, batch=B), warm=1, it=3)
+        print(f"vit B={B}: {ms:.1f} ms -> {B/ms*1e3:.0f} images/s, {B*110.967/ms:.0f} TF/s algorithmic", flush=True)
+
+
 def attn_probe():
     """cross-attention shape of one stage-II chunk: T triplets x 32 rows vs 577 keys, candidate runs of ~91"""
     T, L, Lk, C = 4096, 32, 577, 45
@@ -110,6 +121,8 @@ if __name__ == "__main__":
         gemm_probe()
     if "stage2" in which:
         stage2_probe()
+    if "vit" in which:
+        vit_probe()
     if "stage1" in which:
         stage1_probe()
     if "attn" in which:
