@@ -144,8 +144,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"stage2_rerank_fiq_shape Q={args.queries} K={K} L={L} G={args.gallery} (bounded sample)",
-                       "sample_triplets_per_step": n_trip},
+            "config": {"workload": f"stage2_rerank_fiq_shape: Q={args.queries} queries x K={K} candidates per GPU, L={L} tokens, "
+                                   f"G={args.gallery} gallery images (577 ViT-B/16 tokens each, resident), z_t + stage-II + re-sort + recall",
+                       "sample": f"each step = 1 query x {n_trip} candidates of that workload on the host CPU"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"1 query x {n_trip} candidates per step (z_t + stage-II + sort), fp32, torch CPU {cores} threads"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -231,28 +232,25 @@ def main():
             dist.all_gather(outo, order)
         return scores, order, hits
 
-    # host-resident inputs for the e2e leg
-    ph = lambda t: t.contiguous().pin_memory()
-    h_ref, h_ids, h_mask, h_cand, h_lab = ph(ref), ph(ids), ph(mask), ph(cand), ph(labels.to(torch.uint8))
-    h_scores = torch.empty(Q, K, dtype=torch.float32).pin_memory()
-    h_order = torch.empty(Q, K, dtype=torch.int32).pin_memory()
-    tb = syn.TokenBatch(input_ids=h_ids.long(), attention_mask=h_mask.long())
+    # host-resident inputs for the e2e leg (pinned)
+    tb = syn.TokenBatch(input_ids=ids.long().pin_memory(), attention_mask=mask.long().pin_memory())
     ds = syn.SyntheticRelativeDataset(names, ref, tgt, ["x"] * Q, cand_np, kind="fiq", token_batch=tb)
 
-    def step_e2e():
-        # public API with host buffers: every tensor below is copied H2D inside the call
-        d_ref = h_ref.to(dev, non_blocking=True); d_ids = h_ids.to(dev, non_blocking=True); d_mask = h_mask.to(dev, non_blocking=True)
-        d_lab = h_lab.to(dev, non_blocking=True); d_cand = h_cand.to(dev, non_blocking=True)
-        z_t, _ = m1.encode_queries(tokens, d_ref, d_ids, d_mask, want_z=True, want_emb=False)
-        scores = m2.score_triplets(z_t, d_ids, d_mask, tokens, h_cand.numpy(), row_active)
-        order = eng.rerank_sort(scores)
-        hits = eng.recall_counts(d_lab, order, (10, 50))          # D2H of the recall counters
-        h_scores.copy_(scores, non_blocking=True); h_order.copy_(order, non_blocking=True)
-        torch.cuda.synchronize()
-        return hits
-    h2d = sum(t.numel() * t.element_size() for t in (h_ref, h_ids, h_mask, h_cand, h_lab))
-    d2h = h_scores.numel() * 4 + h_order.numel() * 4 + 16
+    V2 = cir.validate_stage2
 
+    def step_e2e():
+        # the reference's own entry point for this path (src/validate_stage2.py:33-66) on a dataset object whose
+        # token ids / masks / candidate names / labels live in HOST memory: every step re-tokenises from the host
+        # batch, maps names to gallery rows, uploads ids, masks, per-chunk triplet lists and labels (H2D), scores,
+        # re-sorts, and reads the recall counters back (D2H)
+        r10, r50 = V2.compute_fiq_val_metrics(ds, m2, m1, tokens, names)
+        torch.cuda.synchronize()
+        return r10, r50
+    # bytes per step, counted from the tensors the call copies: int64 ids+mask, int32 reference rows, bool labels,
+    # per triplet flat position (8) + query row (4) + candidate slot (4), per-chunk candidate/query lists and
+    # attention work lists (16 B per 8 query tiles + 16 B per 128-row tile + 16 B per 128 CLS rows)
+    h2d = 2 * Q * L * 8 + Q * 4 + Q * K + n_trip * 16 + n_trip * (16 // 4 + 16 // 4 + 1) + 2 * (Q + G) * 4
+    d2h = 2 * 8
     def barrier():
         if world > 1:
             dist.barrier()
@@ -288,6 +286,29 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- secondary figures of the same path (outside the timed region): stage-I candidate filtering
+    #      (BASELINE configs[1]: cosine + top-100 over the 2.3k gallery, Q = 4,181) and ViT token extraction
+    def _time(fn, it=3):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(it):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / it
+    extras = {}
+    if rank == 0:
+        gq = torch.Generator().manual_seed(5)
+        qe = torch.nn.functional.normalize(torch.randn(4181, 256, generator=gq), dim=-1).to(dev)
+        ge = m1.engine.stage1_gallery_embed(m1._w, tokens)
+        ex = torch.randint(0, G, (4181,), generator=gq)
+        ms1 = _time(lambda: eng.stage1_topk(qe, ge, 100, exclude=ex))
+        img = torch.randn(64, 3, 384, 384, device=dev)
+        msv = _time(lambda: eng.vit_forward(m2._vit, img, batch=64), it=2)
+        extras = {"stage1_topk": {"queries_per_s": 4181 / (ms1 / 1e3), "Q": 4181, "G": G, "K": 100, "ms": ms1,
+                                  "note": "fused fp32 1 - q @ G^T + per-query top-100 with the reference index excluded"},
+                  "vit_b16_384": {"images_per_s": 64 / (msv / 1e3), "batch": 64, "ms": msv}}
+
     total_trip = n_trip
     if world > 1:
         t = torch.tensor([float(n_trip)], device=dev)
@@ -318,6 +339,7 @@ def main():
                          "effective_frac_of_peak": value / world * F_REF_GF / 1e3 / peak if peak else None},
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
+            "extras": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
