@@ -110,7 +110,7 @@ def synth_workload(args, rank):
     return ref.int(), tgt, ids.int(), mask.int(), cand, labels
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """Reference arm: the reference's CPU arithmetic (oracle port; the Python reference itself cannot
     travel to the box) on all host threads, each step a bounded sample of the same workload."""
     if rank != 0:
@@ -151,7 +151,7 @@ def run_reference(args, rank, world):
                              "sample": f"1 query x {n_trip} candidates per step (z_t + stage-II + sort), fp32, torch CPU {cores} threads"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(args):
@@ -182,12 +182,23 @@ def cpu_baseline(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else a library prints there (e.g. "NCCL version ..." on the
+    # first collective) is routed to stderr by pointing fd 1 at fd 2 until the line is ready
+    sys.stdout.flush()
+    _stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(_stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
     import cir_b200 as cir
     import torch.distributed as dist
@@ -341,7 +352,7 @@ def main():
             "clocks": sampler.summary(),
             "extras": extras,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
