@@ -19,6 +19,8 @@ struct cir_ctx {
   int attn_impl;        // 0 = auto (tensor cores in bf16 mode), 1 = force the CUDA-core kernel
   int gemm_pair;        // 1 = allow cta_group::2 pair tiles for large GEMMs (default)
   int prune_last;       // 1 = stage II computes the last layer for the CLS rows only (default)
+  int fuse_ln;          // 1 = LayerNorm fused into the N=768 pair-tile GEMM epilogues where eligible (default)
+  const float* ln_gamma; const float* ln_beta; float ln_eps;   // set around ONE cir_gemm call to request the fused LayerNorm
   cudaStream_t stream;
   int num_sms;
   int64_t launches;
@@ -94,4 +96,6 @@ int cir_gemm_simt(cir_ctx* ctx, const cir_gemm_args* a);
 int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a);
 // 2-D bf16 tensor map over a [rows, K] row-major matrix (row stride ld elements), box [box_rows, 64], SWIZZLE_128B
 int cir_make_map_2d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows);
-int cir_attention_tc(cir_ctx* ctx, const cir_attn_args* a);    // attention_tc.cu; CIR_EUNSUPPORTED -> caller falls back
+int cir_attention_tc(cir_ctx* ctx, const cir_attn_args* a);
+// true when cir_gemm_tcgen05 would use the cta_group::2 pair tile for this shape (the fused LayerNorm needs it)
+bool cir_gemm_uses_pair(const cir_ctx* ctx, int64_t M, int64_t N, int batch);    // attention_tc.cu; CIR_EUNSUPPORTED -> caller falls back

@@ -36,7 +36,7 @@ template <int BN, bool PAIR = false> struct Cfg {
   static constexpr int EPI_STAGING = NUM_EPI_WARPS * 4096;   // per-warp 32 x 128 B transpose tiles
   static constexpr int STAGES = (196608 - EPI_STAGING) / STAGE_BYTES;    // 5 (32 KB stages) or 3 (48 KB stages)
   static constexpr int TMEM_COLS = ACC_STAGES * BN;      // 512 / 256
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 192 /*barriers*/ + ACC_STAGES * BN * 4 /*bias*/ + EPI_STAGING;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 192 /*barriers*/ + ACC_STAGES * BN * 4 /*bias*/ + EPI_STAGING + 2 * 128 * 2 * 4 /*LayerNorm row statistics*/;
 };
 
 struct Params {
@@ -47,7 +47,32 @@ struct Params {
   int64_t a_rows_per_batch, w_rows_per_batch;
   int32_t batch, act, c_f32, res_f32;
   int32_t m_blocks, n_blocks, k_blocks, num_tiles;
+  // fused LayerNorm (pair tiles, N == n_blocks*256 == 768, bf16 C): every worker walks all n-tiles of an
+  // m-block back to back, keeps per-row sum / sum of squares, then normalises its rows IN PLACE (re-reading the
+  // just-written pre-LN values from L2).  gamma/beta: fp32 [batch][N].
+  const float* ln_gamma; const float* ln_beta; float ln_eps; int32_t ln_fuse;
 };
+
+// tile sequence of one worker: plain round-robin over tiles, or (LayerNorm fusion) round-robin over m-blocks with the
+// n-tiles of a block visited consecutively
+__device__ __forceinline__ bool next_tile(const Params& p, int worker, int num_workers, int it, int& b, int& m_blk, int& n_blk) {
+  if (p.ln_fuse) {
+    const int unit = worker + (it / p.n_blocks) * num_workers;
+    if (unit >= p.batch * p.m_blocks) return false;
+    n_blk = it % p.n_blocks;
+    b = unit / p.m_blocks;
+    m_blk = unit - b * p.m_blocks;
+    return true;
+  }
+  const int tile = worker + it * num_workers;
+  if (tile >= p.num_tiles) return false;
+  const int tiles_per_batch = p.m_blocks * p.n_blocks;
+  b = tile / tiles_per_batch;
+  const int r = tile - b * tiles_per_batch;
+  m_blk = r / p.n_blocks;
+  n_blk = r - m_blk * p.n_blocks;
+  return true;
+}
 
 // GELU in the bf16 epilogue: the tanh form with the hardware tanh.approx (one MUFU + 6 FMA-pipe ops per
 // element; the erf form costs two MUFU + ~14 ops and made the FFN1 epilogue slower than its MMAs).
@@ -62,7 +87,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 // ----------------------------------------------------------------------------- the kernel
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool LN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p) {
   using C = Cfg<BN, PAIR>;
@@ -105,16 +130,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
-  const int tiles_per_batch = p.m_blocks * p.n_blocks;
-
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = worker; tile < p.num_tiles; tile += num_workers) {
-        const int b = tile / tiles_per_batch;
-        const int r = tile - b * tiles_per_batch;
-        const int m_blk = r / p.n_blocks, n_blk = r - m_blk * p.n_blocks;
+      int b, m_blk, n_blk;
+      for (int it = 0; next_tile(p, worker, num_workers, it, b, m_blk, n_blk); ++it) {
         const int32_t a_row = (int32_t)(b * p.a_rows_per_batch + (int64_t)m_blk * TILE_M + rank * BM);
         const int32_t w_row = (int32_t)(b * p.w_rows_per_batch + (int64_t)n_blk * BN + rank * C::B_ROWS);
         for (int kb = 0; kb < p.k_blocks; kb++) {
@@ -138,7 +159,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = worker; tile < p.num_tiles; tile += num_workers) {
+      int b_, m_, n_;
+      for (int it = 0; next_tile(p, worker, num_workers, it, b_, m_, n_); ++it) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);          // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -192,10 +214,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       return v;
     };
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = worker; tile < p.num_tiles; tile += num_workers) {
-      const int b = tile / tiles_per_batch;
-      const int r = tile - b * tiles_per_batch;
-      const int m_blk = r / p.n_blocks, n_blk = r - m_blk * p.n_blocks;
+    float ln_sum = 0.f, ln_sq = 0.f;                       // fused LayerNorm: this thread's row, this warp's column half
+    float* sstat = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES + 192 + ACC_STAGES * BN * 4 + C::EPI_STAGING);   // [2 halves][128 rows][2]
+    int b, m_blk, n_blk;
+    for (int it = 0; next_tile(p, worker, num_workers, it, b, m_blk, n_blk); ++it) {
       const int64_t row_base = (int64_t)m_blk * TILE_M + rank * BM + quarter * 32;
       const int64_t row = row_base + lane;
       const bool row_ok = row < p.M;
@@ -282,6 +304,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
             for (int q = 0; q < 4; q++) h2[q] = __floats2bfloat162_rn(f[j * 8 + 2 * q], f[j * 8 + 2 * q + 1]);
+            if constexpr (LN) {                             // statistics of the ROUNDED values the in-place pass will read back
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const float2 t = __bfloat1622float2(h2[q]);
+                ln_sum += t.x + t.y;
+                ln_sq = fmaf(t.x, t.x, fmaf(t.y, t.y, ln_sq));
+              }
+            }
             sts128(stg + (uint32_t)lane * 128 + (uint32_t)((j ^ (lane & 7)) << 4), ov);
           }
           __syncwarp();
@@ -333,6 +363,59 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         else mbar_arrive(tempty_bar(acc));
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+
+      if (LN && n_blk == p.n_blocks - 1) {
+        // ---- fused LayerNorm: all N columns of this m-block have been written (by this CTA's epilogue warps, still in
+        // L2).  Combine the two column halves' row statistics, then normalise this warp's 32 rows x (n_blocks x 128)
+        // columns in place with coalesced 16 B accesses.
+        const int rloc = quarter * 32 + lane;
+        sstat[(half * 128 + rloc) * 2] = ln_sum;
+        sstat[(half * 128 + rloc) * 2 + 1] = ln_sq;
+        __threadfence_block();                               // this warp's global stores precede its loads below
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float tot = ln_sum + sstat[((half ^ 1) * 128 + rloc) * 2];
+        const float tsq = ln_sq + sstat[((half ^ 1) * 128 + rloc) * 2 + 1];
+        const float inv_n = 1.0f / (float)p.N;
+        const float mean = tot * inv_n;
+        const float rstd = rsqrtf(fmaxf(tsq * inv_n - mean * mean, 0.f) + p.ln_eps);
+        ln_sum = 0.f; ln_sq = 0.f;
+        const float* gam = p.ln_gamma + (int64_t)b * p.N;
+        const float* bet = p.ln_beta + (int64_t)b * p.N;
+        bf16* cbase = (bf16*)p.C + b * p.c_bstride + lp * 8;
+        for (int nb = 0; nb < p.n_blocks; nb++) {
+#pragma unroll
+          for (int sp = 0; sp < COLS_PER_WARP / 64; sp++) {
+            const int64_t c0 = (int64_t)nb * BN + half * COLS_PER_WARP + sp * 64 + lp * 8;   // this lane's 8 columns
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gam + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gam + c0 + 4));
+            const float4 e0 = __ldg(reinterpret_cast<const float4*>(bet + c0)), e1 = __ldg(reinterpret_cast<const float4*>(bet + c0 + 4));
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+            uint4 raw[8];
+#pragma unroll
+            for (int i8 = 0; i8 < 8; i8++) {               // 8 independent 16 B loads in flight (L2 hits)
+              const int64_t rg = row_base + i8 * 4 + lr;
+              raw[i8] = rg < p.M ? __ldcg(reinterpret_cast<const uint4*>(cbase + rg * p.ldc + (c0 - lp * 8))) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int i8 = 0; i8 < 8; i8++) {
+              const int rr = i8 * 4 + lr;
+              const float mu = __shfl_sync(0xffffffffu, mean, rr);
+              const float rs = __shfl_sync(0xffffffffu, rstd, rr);
+              const int64_t rg = row_base + rr;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&raw[i8]);
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                float2 t = __bfloat1622float2(h2[q]);
+                t.x = fmaf((t.x - mu) * rs, gg[2 * q], bb[2 * q]);
+                t.y = fmaf((t.y - mu) * rs, gg[2 * q + 1], bb[2 * q + 1]);
+                h2[q] = __floats2bfloat162_rn(t.x, t.y);
+              }
+              if (rg < p.M) *reinterpret_cast<uint4*>(cbase + rg * p.ldc + (c0 - lp * 8)) = raw[i8];
+            }
+          }
+        }
+        __syncwarp();
+      }
     }
   }
 
@@ -388,12 +471,12 @@ int cir_make_map_2d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t ro
   return CIR_OK;
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool LN>
 static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, const CUtensorMap& mw) {
   using C = tc::Cfg<BN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    CIR_CUDA(cudaFuncSetAttribute(tc::gemm_tcgen05_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CIR_CUDA(cudaFuncSetAttribute(tc::gemm_tcgen05_kernel<BN, PAIR, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int slots = PAIR ? ctx->num_sms / 2 : ctx->num_sms;
@@ -411,11 +494,16 @@ static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, c
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cir_prof_gemm_begin(ctx, 2.0 * (double)p.M * (double)p.N * (double)p.K * (double)p.batch);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_tcgen05_kernel<BN, PAIR>, ma, mw, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_tcgen05_kernel<BN, PAIR, LN>, ma, mw, p);
   cir_prof_gemm_end(ctx);
   if (e != cudaSuccess) { cir_set_error("tcgen05 GEMM launch failed: %s", cudaGetErrorString(e)); return CIR_ECUDA; }
   CIR_LAUNCH_CHECK(ctx);
   return CIR_OK;
+}
+
+bool cir_gemm_uses_pair(const cir_ctx* ctx, int64_t M, int64_t N, int batch) {
+  const int64_t pair_tiles = ((M + 2 * tc::BM - 1) / (2 * tc::BM)) * ((N + 255) / 256) * batch;
+  return ctx->gemm_pair && pair_tiles >= ctx->num_sms / 2;
 }
 
 int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a) {
@@ -450,10 +538,16 @@ int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a) {
   const int64_t nt = (int64_t)p.m_blocks * p.n_blocks * a->batch;
   CIR_CHECK_ARG(nt < (1ll << 31), "tcgen05 GEMM: too many tiles");
   p.num_tiles = (int32_t)nt;
+  p.ln_gamma = ctx->ln_gamma; p.ln_beta = ctx->ln_beta; p.ln_eps = ctx->ln_eps;
+  p.ln_fuse = (ctx->ln_gamma != nullptr) ? 1 : 0;
+  if (p.ln_fuse) {
+    CIR_CHECK_ARG(use_pair && !a->c_f32 && a->N == 768 && (a->ldc % 8) == 0 && a->act == CIR_ACT_NONE,
+                  "fused LayerNorm needs a pair-tile GEMM with N = 768 and a bf16 output");
+  }
   CUtensorMap ma, mw;
   CIR_TRY(cir_make_map_2d(ctx, &ma, a->A, a_rows, a->K, a->lda, tc::BM));
   CIR_TRY(cir_make_map_2d(ctx, &mw, a->W, w_rows, a->K, a->ldw, use_pair ? BN / 2 : BN));
-  if (use_pair) return launch_tc<256, true>(ctx, p, ma, mw);
-  if (use128) return launch_tc<128, false>(ctx, p, ma, mw);
-  return launch_tc<256, false>(ctx, p, ma, mw);
+  if (use_pair) return p.ln_fuse ? launch_tc<256, true, true>(ctx, p, ma, mw) : launch_tc<256, true, false>(ctx, p, ma, mw);
+  if (use128) return launch_tc<128, false, false>(ctx, p, ma, mw);
+  return launch_tc<256, false, false>(ctx, p, ma, mw);
 }

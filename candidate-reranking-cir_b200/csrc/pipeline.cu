@@ -68,6 +68,8 @@ extern "C" int cir_create(cir_ctx** out, int device, int dtype) {
   c->attn_impl = 0;
   c->gemm_pair = 1;
   c->prune_last = 1;
+  c->fuse_ln = 0;   // measured on B200: no gain over the separate HBM-bound LayerNorm kernels, so opt-in
+  c->ln_gamma = nullptr; c->ln_beta = nullptr; c->ln_eps = 0.f;
   c->stream = 0;
   c->num_sms = prop.multiProcessorCount;
   c->launches = 0;
@@ -117,6 +119,7 @@ extern "C" int cir_set_attention_impl(cir_ctx* ctx, int impl) {
   return CIR_OK;
 }
 extern "C" int cir_set_prune_last_layer(cir_ctx* ctx, int enable) { ctx->prune_last = enable ? 1 : 0; return CIR_OK; }
+extern "C" int cir_set_fuse_layernorm(cir_ctx* ctx, int enable) { ctx->fuse_ln = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_get_dtype(const cir_ctx* ctx) { return ctx->dtype; }
 extern "C" int64_t cir_launch_count(cir_ctx* ctx, int reset) {
   int64_t n = ctx->launches;
@@ -159,6 +162,28 @@ int gemm(cir_ctx* ctx, const void* A, int64_t lda, int64_t a_bs, const void* W, 
 }
 
 inline char* at(void* p, int64_t elems, size_t esz) { return (char*)p + elems * (int64_t)esz; }
+
+// y = LayerNorm(A W^T + bias + res) with per-batch gamma/beta [batch][N=768], rows contiguous (ld = 768).
+// bf16 mode with a pair-tile GEMM: ONE kernel (statistics and in-place normalisation inside the GEMM epilogue);
+// otherwise GEMM into `pre` followed by the LayerNorm kernel.
+int gemm_layernorm(cir_ctx* ctx, const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw, int64_t w_bs, const float* bias,
+                   int64_t bias_bs, const void* res, int64_t ldres, int64_t res_bs, const float* gamma, const float* beta, float eps,
+                   void* pre, void* y, int64_t M, int64_t K, int batch) {
+  const int64_t D_ = CIR_HIDDEN;
+  // Fusing pays only where the epilogue has slack: with K = 3072 (FFN2) a tile's MMAs take 4x longer than its epilogue,
+  // so the in-place normalisation pass is free; with K = 768 the epilogue is already the pacing stage and the extra
+  // pass costs more than the separate (HBM-bound) LayerNorm kernel it would replace (measured).
+  const bool fused = ctx->dtype == CIR_DTYPE_BF16 && ctx->fuse_ln && ctx->gemm_impl != CIR_GEMM_SIMT && (K % 8) == 0 && K >= 2048 &&
+                     cir_gemm_uses_pair(ctx, M, D_, batch);
+  if (fused) {
+    ctx->ln_gamma = gamma; ctx->ln_beta = beta; ctx->ln_eps = eps;
+    const int rc = gemm(ctx, A, lda, a_bs, W, ldw, w_bs, bias, bias_bs, y, D_, M * D_, 0, res, ldres, res_bs, 0, M, D_, K, batch, CIR_ACT_NONE);
+    ctx->ln_gamma = nullptr; ctx->ln_beta = nullptr;
+    return rc;
+  }
+  CIR_TRY(gemm(ctx, A, lda, a_bs, W, ldw, w_bs, bias, bias_bs, pre, D_, M * D_, 0, res, ldres, res_bs, 0, M, D_, K, batch, CIR_ACT_NONE));
+  return cir_add_layernorm(ctx, pre, 0, (int64_t)batch * M, nullptr, gamma, beta, M, y, 0, (int64_t)batch * M, eps);
+}
 
 constexpr int64_t D = CIR_HIDDEN, F = CIR_FFN;
 constexpr float BERT_EPS = 1e-12f;   // configs/med_config.json:11
@@ -370,9 +395,8 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
       CIR_TRY(cir_attention(ctx, &a));
     }
     // a_s = LayerNorm{A,B}(dense_s(ctx_s) + h_s)   (:261-264)
-    CIR_TRY(gemm(ctx, ws.ctx, D, M * D, w->self_out_w[i], D, D * D, w->self_out_b[i], D, ws.pre, D, M * D, 0, ws.h, D, M * D, 0,
-                 M, D, D, 2, CIR_ACT_NONE));
-    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 0, 2 * M, nullptr, w->self_ln_g[i], w->self_ln_b[i], M, ws.a, 0, 2 * M, BERT_EPS));
+    CIR_TRY(gemm_layernorm(ctx, ws.ctx, D, M * D, w->self_out_w[i], D, D * D, w->self_out_b[i], D, ws.h, D, M * D,
+                           w->self_ln_g[i], w->self_ln_b[i], BERT_EPS, ws.pre, ws.a, M, D, 2));
     // ---- twin cross-attention onto the SAME candidate tokens (:322-339)
     CIR_TRY(gemm(ctx, ws.a, D, M * D, w->cross_q_w[i], D, D * D, w->cross_q_b[i], D, ws.qc, D, M * D, 0, nullptr, 0, 0, 0,
                  M, D, D, 2, CIR_ACT_NONE));
@@ -396,8 +420,8 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
     CIR_TRY(cir_add_layernorm(ctx, ws.m, 0, M, ws.a, w->cross_ln_g[i], w->cross_ln_b[i], M, ws.x, 0, 2 * M, BERT_EPS));
     // ---- FFN, weights shared by both streams (:469-476): both streams as 2M rows
     CIR_TRY(gemm(ctx, ws.x, D, 0, w->ffn1_w[i], D, 0, w->ffn1_b[i], 0, ws.f, F, 0, 0, nullptr, 0, 0, 0, 2 * M, F, D, 1, CIR_ACT_GELU));
-    CIR_TRY(gemm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.pre, D, 0, 0, ws.x, D, 0, 0, 2 * M, D, F, 1, CIR_ACT_NONE));
-    CIR_TRY(cir_add_layernorm(ctx, ws.pre, 0, 2 * M, nullptr, w->ffn_ln_g[i], w->ffn_ln_b[i], 2 * M, ws.h, 0, 2 * M, BERT_EPS));
+    CIR_TRY(gemm_layernorm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.x, D, 0, w->ffn_ln_g[i], w->ffn_ln_b[i], BERT_EPS,
+                           ws.pre, ws.h, 2 * M, F, 1));
   }
   if (ctx->prune_last) {
     // ---- last layer, CLS rows only.  The encoder returns cat(h0[:,0,:], h1[:,0,:]) (nlvr_encoder.py:906-909), so

@@ -140,3 +140,49 @@ def test_stage1_driver_on_synthetic_dataset(small):
     r1, r5, r10, r50, topk = V1.compute_cirr_val_metrics(ds, m1, tokens1, g_emb, names, k=K)
     assert topk["sorted_index_names"].shape[0] == Q and topk["labels"].shape[0] == Q
     assert 0.0 <= r1 <= r5 <= r10 <= r50 <= 100.0
+
+
+def test_fused_layernorm_matches_separate_kernels():
+    """LayerNorm fused into the pair-tile GEMM epilogue (statistics + in-place pass) vs GEMM + LayerNorm kernel on a
+    chunk large enough for pair tiles (M = T*L = 16384 rows)."""
+    syn_ = cir.synthetic
+    sd2 = golden_weights(load_golden("pipeline_small.npz"))[1]
+    m2 = cir.blip_stage2.blip_stage2(image_size=384, state_dict=sd2, precision="bf16")
+    eng = m2.engine
+    g = torch.Generator().manual_seed(5)
+    G, Q, K, L = 12, 64, 8, 32
+    tokens = torch.randn(G, 577, 768, generator=g).cuda().bfloat16()
+    ids, mask = syn_.make_token_ids(Q, L, seed=2, min_len=20)
+    ids[:, 0] = syn_.ENC_TOKEN_ID
+    z_t = torch.randn(Q, L, 768, generator=g).cuda().bfloat16()
+    cand = torch.stack([torch.randperm(G, generator=g)[:K] for _ in range(Q)]).int().numpy()
+    b = m2.score_triplets(z_t, ids, mask, tokens, cand)
+    eng.set_fuse_layernorm(True)
+    try:
+        a = m2.score_triplets(z_t, ids, mask, tokens, cand)
+    finally:
+        eng.set_fuse_layernorm(False)
+    assert torch.isfinite(a).all()
+    assert (a - b).abs().max() < 2e-2, (a - b).abs().max()        # both are bf16 paths: differences are rounding noise
+
+
+def test_large_chunk_vs_oracle():
+    """A chunk big enough for the cta_group::2 pair tiles, the fused GEMM+LayerNorm epilogue and full 128-row attention
+    tiles (T = 104 triplets x 32 rows) against the CPU oracle: |score diff| <= 2e-2."""
+    syn_ = cir.synthetic
+    g0 = load_golden("pipeline_small.npz")
+    sd1, sd2 = golden_weights(g0)
+    m2 = cir.blip_stage2.blip_stage2(image_size=384, state_dict=sd2, precision="bf16")
+    g = torch.Generator().manual_seed(6)
+    G, Q, K, L = 3, 13, 8, 32
+    tokens = torch.randn(G, 577, 768, generator=g).cuda().bfloat16()
+    ids, mask = syn_.make_token_ids(Q, L, seed=3, min_len=18)
+    ids[:, 0] = syn_.ENC_TOKEN_ID
+    z_t = torch.randn(Q, L, 768, generator=g).cuda().bfloat16()
+    cand = torch.stack([torch.randint(0, G, (K,), generator=g) for _ in range(Q)]).int()      # heavy candidate reuse
+    s = m2.score_triplets(z_t, ids, mask, tokens, cand.numpy())
+    tok_ref, z_ref = tokens.float().cpu(), z_t.float().cpu()
+    with torch.no_grad():
+        want = torch.stack([O.stage2_score(sd2, z_ref[q:q + 1], ids[q:q + 1], mask[q:q + 1], tok_ref[cand[q].long()]) for q in range(Q)])
+    err = (s.cpu() - want).abs()
+    assert err.max() <= 2e-2, (err.max(), err.mean())
