@@ -284,6 +284,138 @@ attention_mma_kernel(cir_attn_args p, int mt) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// attention_small_kernel: masked text self-attention with Lq, Lk <= 32 (the twin self-attention of the dual-stream
+// encoder at the BASELINE caption length).  It is bound by re-reading the QKV projection from HBM, so the kernel is
+// built for memory-level parallelism: ONE WARP per (batch, head), no block barriers, Q and K fragments loaded straight
+// from global memory into mma.sync operand registers, V staged through a warp-private swizzled 4 KB tile for
+// ldmatrix.trans, exact single-pass softmax (all 32 keys are in registers).
+constexpr int SM_WARPS = 4;
+__global__ void __launch_bounds__(SM_WARPS * 32)
+attention_small_kernel(cir_attn_args p) {
+  __shared__ __align__(128) uint8_t sv_all[SM_WARPS][32 * 128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t wid = (int64_t)blockIdx.x * SM_WARPS + warp;
+  if (wid >= (int64_t)p.B * p.H) return;
+  const int b = (int)(wid / p.H), h = (int)(wid % p.H);
+  const int kvb = p.kv_index ? p.kv_index[b] : b;
+  const bf16* Qb = (const bf16*)p.q + (int64_t)b * p.q_bs + h * DH;
+  const bf16* Kg = (const bf16*)p.k + (int64_t)kvb * p.k_bs + h * DH;
+  const bf16* Vg = (const bf16*)p.v + (int64_t)kvb * p.v_bs + h * DH;
+  bf16* Ob = (bf16*)p.o + (int64_t)b * p.o_bs + h * DH;
+  const int32_t* mask = p.key_mask ? p.key_mask + (int64_t)(p.mask_index ? p.mask_index[b] : b) * p.Lk : nullptr;
+  // ---- V rows -> warp-private swizzled tile (issued first: longest latency)
+  uint8_t* sv = sv_all[warp];
+  {
+    uint4 vv[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int row = i * 4 + (lane >> 3), ch = lane & 7;
+      vv[i] = row < p.Lk ? *reinterpret_cast<const uint4*>(Vg + (int64_t)row * p.v_rs + ch * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int row = i * 4 + (lane >> 3), ch = lane & 7;
+      *reinterpret_cast<uint4*>(sv + row * 128 + ((ch ^ (row & 7)) << 4)) = vv[i];
+    }
+  }
+  // ---- K fragments (B operand of Q K^T): n-tile j = keys 8j..8j+7, k-step kk = dh 16kk..16kk+15
+  uint32_t kb[4][4][2];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int key = j * 8 + g;
+    const uint32_t* kp = reinterpret_cast<const uint32_t*>(Kg + (int64_t)key * p.k_rs);
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      kb[j][kk][0] = key < p.Lk ? kp[kk * 8 + t] : 0u;
+      kb[j][kk][1] = key < p.Lk ? kp[kk * 8 + 4 + t] : 0u;
+    }
+  }
+  // per-thread additive mask (log2 domain) of its 8 key columns: keys 8j + 2t + e
+  const float sl2 = p.scale * 1.4426950408889634f;
+  float madd[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int key = j * 8 + 2 * t + e;
+      madd[j][e] = key >= p.Lk ? -INFINITY : ((mask && mask[key] == 0) ? -10000.0f * 1.4426950408889634f : 0.f);
+    }
+  __syncwarp();
+  const uint32_t sv_addr = (uint32_t)__cvta_generic_to_shared(sv);
+#pragma unroll 1
+  for (int mt = 0; mt < 2; mt++) {
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    if (mt * 16 >= p.Lq) break;
+    const bool v0 = r0 < p.Lq, v1 = r1 < p.Lq;
+    uint32_t qa[4][4];
+    {
+      const uint32_t* q0 = reinterpret_cast<const uint32_t*>(Qb + (int64_t)r0 * p.q_rs);
+      const uint32_t* q1 = reinterpret_cast<const uint32_t*>(Qb + (int64_t)r1 * p.q_rs);
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        qa[kk][0] = v0 ? q0[kk * 8 + t] : 0u;
+        qa[kk][1] = v1 ? q1[kk * 8 + t] : 0u;
+        qa[kk][2] = v0 ? q0[kk * 8 + 4 + t] : 0u;
+        qa[kk][3] = v1 ? q1[kk * 8 + 4 + t] : 0u;
+      }
+    }
+    float sc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) mma_bf16_16816(sc[j], qa[kk], kb[j][kk][0], kb[j][kk][1]);
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        sc[j][e] = fmaf(sc[j][e], sl2, madd[j][e]);
+        sc[j][2 + e] = fmaf(sc[j][2 + e], sl2, madd[j][e]);
+        m0 = fmaxf(m0, sc[j][e]);
+        m1 = fmaxf(m1, sc[j][2 + e]);
+      }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+    uint32_t pa[2][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float p00 = exp2f(sc[j][0] - m0), p01 = exp2f(sc[j][1] - m0);
+      const float p10 = exp2f(sc[j][2] - m1), p11 = exp2f(sc[j][3] - m1);
+      l0 += p00 + p01; l1 += p10 + p11;
+      pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p00, p01);
+      pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p10, p11);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 2; kk++) {
+      const int vrow = kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+      const uint32_t rowaddr = sv_addr + (uint32_t)vrow * 128;
+#pragma unroll
+      for (int jp = 0; jp < 4; jp++) {
+        uint32_t vb[4];
+        ldmatrix_x4_trans(rowaddr + (uint32_t)(((2 * jp + (lane >> 4)) ^ (vrow & 7)) << 4), vb);
+        mma_bf16_16816(o[2 * jp], pa[kk], vb[0], vb[1]);
+        mma_bf16_16816(o[2 * jp + 1], pa[kk], vb[2], vb[3]);
+      }
+    }
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (v0) *reinterpret_cast<uint32_t*>(Ob + (int64_t)r0 * p.o_rs + j * 8 + 2 * t) = pack_bf16(o[j][0] * i0, o[j][1] * i0);
+      if (v1) *reinterpret_cast<uint32_t*>(Ob + (int64_t)r1 * p.o_rs + j * 8 + 2 * t) = pack_bf16(o[j][2] * i1, o[j][3] * i1);
+    }
+  }
+}
+
 template <int NWARPS>
 int launch_mma(cir_ctx* ctx, const cir_attn_args* a, int mt) {
   const int cpb = (mt + NWARPS - 1) / NWARPS;
@@ -321,6 +453,12 @@ extern "C" int cir_attention(cir_ctx* ctx, const cir_attn_args* a) {
                   ((uintptr_t)a->k & 15) == 0 && ((uintptr_t)a->v & 15) == 0 && ((uintptr_t)a->q & 3) == 0 && ((uintptr_t)a->o & 3) == 0,
                   "attention: operand strides/alignment not supported by the tensor-core kernel");
     const int mt = (a->Lq + 15) / 16;
+    if (!a->work && a->Lq <= 32 && a->Lk <= 32 && a->Lq > 1 && ctx->attn_impl == 0) {      // masked text self-attention
+      const int64_t warps = (int64_t)a->B * a->H;
+      attention_small_kernel<<<(unsigned)((warps + SM_WARPS - 1) / SM_WARPS), SM_WARPS * 32, 0, ctx->stream>>>(*a);
+      CIR_LAUNCH_CHECK(ctx);
+      return CIR_OK;
+    }
     if (a->work) { CIR_CHECK_ARG(a->num_work > 0, "attention: empty work list"); return launch_mma<8>(ctx, a, mt); }
     if (mt <= 2) return launch_mma<2>(ctx, a, mt);
     if (mt <= 4) return launch_mma<4>(ctx, a, mt);
