@@ -58,3 +58,32 @@ def test_empty_inputs(models):
     assert td.shape == (0, 3)
     td, ti = eng.stage1_topk(torch.nn.functional.normalize(torch.randn(2, 256), dim=-1), torch.nn.functional.normalize(torch.randn(3, 256), dim=-1), 5)
     assert (ti[:, 3:] == -1).all() and torch.isinf(td[:, 3:]).all()        # fewer gallery rows than K
+
+
+def test_max_sizes_sort_and_topk():
+    eng = cir.engine.get_engine(precision="bf16")
+    g = torch.Generator().manual_seed(21)
+    s = torch.randn(3, 2048, generator=g)
+    s[:, 100:200] = s[:, :1]                                  # a block of ties
+    assert torch.equal(eng.rerank_sort(s).cpu().long(), O.rerank_order(s))
+    q = torch.nn.functional.normalize(torch.randn(4, 256, generator=g), dim=-1)
+    gal = torch.nn.functional.normalize(torch.randn(6000, 256, generator=g), dim=-1)
+    dist = 1 - q @ gal.T
+    td, ti = eng.topk_from_dist(dist, 1024)
+    wd, wi = O.stage1_topk(q, gal, None, 1024)
+    assert torch.equal(ti.cpu().long(), wi) and torch.equal(td.cpu(), wd)
+
+
+def test_vit_other_image_size():
+    """224 px (197 tokens): the ViT path is not specialised to 384 px."""
+    sd = syn.make_stage2_state_dict(3, 224, "dense")
+    m = cir.blip_stage2.blip_stage2(image_size=224, state_dict=sd, precision="fp32")
+    images = syn.make_images(2, 224, seed=5)
+    tok = m.img_embed(images)
+    assert tok.shape == (2, 197, 768)
+    with torch.no_grad():
+        want = O.vit_forward(sd, images)
+    assert (tok.cpu() - want).abs().max() < 2e-4
+    mb = cir.blip_stage2.blip_stage2(image_size=224, state_dict=sd, precision="bf16")
+    tb = mb.img_embed(images).float().cpu()
+    assert (tb - want).abs().mean() < 0.02
