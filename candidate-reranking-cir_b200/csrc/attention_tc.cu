@@ -207,11 +207,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_cons
       tmem_ld_wait();
       // ---- row max of the chunk
       float cmax = -INFINITY;
-      if (full_chunk) {
+      if (full_chunk) {                                      // four independent FMNMX3 chains (8 deep instead of 32)
+        float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) cmax = max3(cmax, __uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) cmax = max3(cmax, __uint_as_float(v1[i]), __uint_as_float(v1[i + 1]));
+        for (int i = 0; i < 16; i += 2) {
+          c0 = max3(c0, __uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
+          c1 = max3(c1, __uint_as_float(v0[16 + i]), __uint_as_float(v0[17 + i]));
+          c2 = max3(c2, __uint_as_float(v1[i]), __uint_as_float(v1[i + 1]));
+          c3 = max3(c3, __uint_as_float(v1[16 + i]), __uint_as_float(v1[17 + i]));
+        }
+        cmax = fmaxf(max3(c0, c1, c2), c3);
       } else {
 #pragma unroll
         for (int i = 0; i < 32; i++) if (i < keys) cmax = fmaxf(cmax, __uint_as_float(v0[i]));
