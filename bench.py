@@ -320,6 +320,32 @@ def main():
                                   "note": "fused fp32 1 - q @ G^T + per-query top-100 with the reference index excluded"},
                   "vit_b16_384": {"images_per_s": 64 / (msv / 1e3), "batch": 64, "ms": msv}}
 
+        # the reference's per-query formulation on stock PyTorch (ATen / cuBLAS) on this same B200: the oracle's torch
+        # code with weights and inputs moved to the GPU -- the library baseline SURVEY 8(d) asks for, since the
+        # reference ships no Blackwell kernel.  Bounded sample: 4 queries x K candidates, fp32 and bf16 autocast.
+        try:
+            from oracle import cir_oracle as O
+            sd1c = {k: v.to(dev) for k, v in syn.make_stage1_state_dict(0, 384, "reference").items()}
+            sd2c = {k: v.to(dev) for k, v in syn.make_stage2_state_dict(0, 384, "reference").items()}
+            tok32 = tokens[: K + 1].float()
+            ids_l, mask_l = ids_d[:4].long(), mask_d[:4].long()
+
+            def torch_pass():
+                with torch.no_grad():
+                    for q in range(4):
+                        z = O.stage1_hidden(sd1c, tok32[:1], ids_l[q:q + 1], mask_l[q:q + 1])
+                        sc = O.stage2_score(sd2c, z, ids_l[q:q + 1], mask_l[q:q + 1], tok32[1:])
+                        torch.argsort(sc, descending=True)
+            ms32 = _time(torch_pass, it=2)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                ms16 = _time(torch_pass, it=2)
+            extras["stock_pytorch_b200"] = {"fp32_triplets_per_s": 4 * K / (ms32 / 1e3), "bf16_autocast_triplets_per_s": 4 * K / (ms16 / 1e3),
+                                            "sample": f"4 queries x {K} candidates, per-query loop as in src/validate_stage2.py:94-125 (z_t + "
+                                                      "img_txt_fusion_val + argsort), oracle torch code on cuda"}
+            del sd1c, sd2c, tok32
+        except Exception as ex:                                  # never let a baseline leg break the bench line
+            extras["stock_pytorch_b200"] = {"error": repr(ex)[:200]}
+
     total_trip = n_trip
     if world > 1:
         t = torch.tensor([float(n_trip)], device=dev)

@@ -186,3 +186,27 @@ def test_large_chunk_vs_oracle():
         want = torch.stack([O.stage2_score(sd2, z_ref[q:q + 1], ids[q:q + 1], mask[q:q + 1], tok_ref[cand[q].long()]) for q in range(Q)])
     err = (s.cpu() - want).abs()
     assert err.max() <= 2e-2, (err.max(), err.mean())
+
+
+def test_bf16_vs_fp32_check_mode_at_scale():
+    """Same weights, same inputs, 1,600 triplets in full-size chunks: the bf16 production path against the fp32 check
+    mode of this library (itself within 1e-4 of the reference): the whole error distribution stays inside 2e-2."""
+    syn_ = cir.synthetic
+    g0 = load_golden("pipeline_small.npz")
+    sd1, sd2 = golden_weights(g0)
+    m16 = cir.blip_stage2.blip_stage2(image_size=384, state_dict=sd2, precision="bf16")
+    m32 = cir.blip_stage2.blip_stage2(image_size=384, state_dict=sd2, precision="fp32")
+    g = torch.Generator().manual_seed(8)
+    G, Q, K, L = 24, 32, 50, 32
+    tokens = torch.randn(G, 577, 768, generator=g).cuda()
+    tokens16 = tokens.bfloat16()
+    tokens32 = tokens16.float()                                # identical (bf16-representable) inputs for both modes
+    ids, mask = syn_.make_token_ids(Q, L, seed=4, min_len=12)
+    ids[:, 0] = syn_.ENC_TOKEN_ID
+    z16 = torch.randn(Q, L, 768, generator=g).cuda().bfloat16()
+    cand = torch.stack([torch.randperm(G, generator=g)[:K] if K <= G else torch.randint(0, G, (K,), generator=g) for _ in range(Q)]).int().numpy() \
+        if K <= G else torch.randint(0, G, (Q, K), generator=g).int().numpy()
+    a = m16.score_triplets(z16, ids, mask, tokens16, cand)
+    b = m32.score_triplets(z16.float(), ids, mask, tokens32, cand)
+    err = (a - b).abs()
+    assert err.max() <= 2e-2 and err.mean() < 5e-3, (err.max().item(), err.mean().item())
