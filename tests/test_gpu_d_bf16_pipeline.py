@@ -204,8 +204,7 @@ def test_bf16_vs_fp32_check_mode_at_scale():
     ids, mask = syn_.make_token_ids(Q, L, seed=4, min_len=12)
     ids[:, 0] = syn_.ENC_TOKEN_ID
     z16 = torch.randn(Q, L, 768, generator=g).cuda().bfloat16()
-    cand = torch.stack([torch.randperm(G, generator=g)[:K] if K <= G else torch.randint(0, G, (K,), generator=g) for _ in range(Q)]).int().numpy() \
-        if K <= G else torch.randint(0, G, (Q, K), generator=g).int().numpy()
+    cand = torch.randint(0, G, (Q, K), generator=g).int().numpy()          # K > G: heavy candidate reuse, duplicates allowed
     a = m16.score_triplets(z16, ids, mask, tokens16, cand)
     b = m32.score_triplets(z16.float(), ids, mask, tokens32, cand)
     err = (a - b).abs()
