@@ -19,6 +19,7 @@ struct cir_ctx {
   int attn_impl;        // 0 = auto (tensor cores in bf16 mode), 1 = force the CUDA-core kernel
   int gemm_pair;        // 1 = allow cta_group::2 pair tiles for large GEMMs (default)
   int prune_last;       // 1 = stage II computes the last layer for the CLS rows only (default)
+  int gemm_tma_store;   // 1 = bf16 GEMM outputs leave through TMA bulk tensor stores (default)
   int fuse_ln;          // 1 = LayerNorm fused into the N=768 pair-tile GEMM epilogues where eligible (default)
   const float* ln_gamma; const float* ln_beta; float ln_eps;   // set around ONE cir_gemm call to request the fused LayerNorm
   cudaStream_t stream;

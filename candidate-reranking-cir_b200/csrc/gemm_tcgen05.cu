@@ -47,6 +47,7 @@ struct Params {
   int64_t a_rows_per_batch, w_rows_per_batch;
   int32_t batch, act, c_f32, res_f32;
   int32_t m_blocks, n_blocks, k_blocks, num_tiles;
+  int32_t tma_store;       // 1: bf16 C tiles leave through cp.async.bulk.tensor stores (3-D map: N, M, batch)
   // fused LayerNorm (pair tiles, N == n_blocks*256 == 768, bf16 C): every worker walks all n-tiles of an
   // m-block back to back, keeps per-row sum / sum of squares, then normalises its rows IN PLACE (re-reading the
   // just-written pre-LN values from L2).  gamma/beta: fp32 [batch][N].
@@ -89,7 +90,8 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // ----------------------------------------------------------------------------- the kernel
 template <int BN, bool PAIR, bool LN>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_c, const Params p) {
   using C = Cfg<BN, PAIR>;
   constexpr int TILE_M = PAIR ? 2 * BM : BM;                 // rows of one scheduled tile
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;       // 0 = leader (issues the MMAs)
@@ -99,7 +101,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + C::STAGES * C::A_BYTES;
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES + C::EPI_STAGING;   // [ring][epilogue staging][barriers][bias][LN stats]
   // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
@@ -107,7 +109,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + ACC_STAGES + s); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * C::STAGES + 2 * ACC_STAGES);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_gen + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 2 * ACC_STAGES));
+  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_gen + C::STAGES * C::STAGE_BYTES + C::EPI_STAGING + 8 * (2 * C::STAGES + 2 * ACC_STAGES));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -198,8 +200,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int half = ew >> 2;                // which half of the BN columns
     constexpr int COLS_PER_WARP = BN / 2;
     constexpr int NCH = COLS_PER_WARP / 32;  // 4 or 2 (even)
-    float* sbias = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES + 192);                  // [ACC_STAGES][BN]
-    const uint32_t stg = bar_base + 192 + ACC_STAGES * BN * 4 + (uint32_t)ew * 4096;                      // this warp's 32 x 128 B tile
+    float* sbias = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::EPI_STAGING + 192);   // [ACC_STAGES][BN]
+    const uint32_t stg = smem_base + C::STAGES * C::STAGE_BYTES + (uint32_t)ew * 4096;                    // this warp's 32 x 128 B tile (4 KB aligned)
     const int etid = threadIdx.x - 64;       // 0..255
     const bool res_bf16_fast = p.residual && !p.res_f32 && (p.ldres & 7) == 0;
     const bool out_bf16_fast = !p.c_f32 && (p.ldc & 7) == 0;
@@ -214,8 +216,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       return v;
     };
     int acc = 0; uint32_t acc_phase = 0;
+    bool tma_store_pending = false;
     float ln_sum = 0.f, ln_sq = 0.f;                       // fused LayerNorm: this thread's row, this warp's column half
-    float* sstat = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES + 192 + ACC_STAGES * BN * 4 + C::EPI_STAGING);   // [2 halves][128 rows][2]
+    float* sstat = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::EPI_STAGING + 192 + ACC_STAGES * BN * 4);   // [2 halves][128 rows][2]
     int b, m_blk, n_blk;
     for (int it = 0; next_tile(p, worker, num_workers, it, b, m_blk, n_blk); ++it) {
       const int64_t row_base = (int64_t)m_blk * TILE_M + rank * BM + quarter * 32;
@@ -274,6 +277,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         if (p.residual) {
           if (res_fast) {
+            if (tma_store_pending) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
+              tma_store_pending = false;
+            }
 #pragma unroll
             for (int it = 0; it < 8; it++) sts128(stg + (uint32_t)(it * 4 + lr) * 128 + (uint32_t)((lp ^ ((it * 4 + lr) & 7)) << 4), rq[it]);
             __syncwarp();
@@ -297,6 +305,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
         }
         // ---- store
+        if (tma_store_pending) {                             // the previous span's TMA store must have read the staging tile
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+          tma_store_pending = false;
+        }
         if (out_bf16_fast && span_full) {
 #pragma unroll
           for (int j = 0; j < 8; j++) {
@@ -314,16 +327,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             sts128(stg + (uint32_t)lane * 128 + (uint32_t)((j ^ (lane & 7)) << 4), ov);
           }
-          __syncwarp();
-          bf16* cp = (bf16*)p.C + b * p.c_bstride + n00 + lp * 8;
+          if (!LN && p.tma_store) {
+            // the staged 32 x 128 B tile already has the SWIZZLE_128B layout: hand it to the TMA engine (rows beyond M
+            // are clipped by the tensor map) instead of spending 8 LDS + 8 STG per lane on it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                           ::"l"(&map_c), "r"(stg), "r"((int32_t)n00), "r"((int32_t)row_base), "r"((int32_t)b) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            tma_store_pending = true;
+          } else {
+            __syncwarp();
+            bf16* cp = (bf16*)p.C + b * p.c_bstride + n00 + lp * 8;
 #pragma unroll
-          for (int it = 0; it < 8; it++) {
-            const int rr = it * 4 + lr;
-            const uint4 ov = lds128(stg + (uint32_t)rr * 128 + (uint32_t)((lp ^ (rr & 7)) << 4));
-            const int64_t rg = row_base + rr;
-            if (rg < p.M) *reinterpret_cast<uint4*>(cp + rg * p.ldc) = ov;
+            for (int it = 0; it < 8; it++) {
+              const int rr = it * 4 + lr;
+              const uint4 ov = lds128(stg + (uint32_t)rr * 128 + (uint32_t)((lp ^ (rr & 7)) << 4));
+              const int64_t rg = row_base + rr;
+              if (rg < p.M) *reinterpret_cast<uint4*>(cp + rg * p.ldc) = ov;
+            }
+            __syncwarp();
           }
-          __syncwarp();
         } else if (out_f32_fast && span_full) {
 #pragma unroll
           for (int hh = 0; hh < 2; hh++) {                  // 32 fp32 columns = 128 B per row per pass
@@ -419,6 +445,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   }
 
+  if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // outstanding TMA stores
   tcgen05_fence_before();
   __syncwarp();
   if constexpr (PAIR) cluster_sync_all();      // no CTA may exit (or free TMEM) while its peer can still signal it
@@ -471,8 +498,22 @@ int cir_make_map_2d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t ro
   return CIR_OK;
 }
 
+// 3-D bf16 tensor map over C: (N, M, batch), box [1, 32 rows, 64 cols], SWIZZLE_128B -- one epilogue warp's staging tile
+static int make_map_c(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t N, int64_t M, int64_t batch, int64_t ldc, int64_t c_bstride) {
+  PFN_encodeTiled enc;
+  CIR_TRY(get_encode_fn(ctx, &enc));
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ldc * 2, (cuuint64_t)(batch > 1 ? c_bstride : M * ldc) * 2};
+  cuuint32_t box[3] = {64, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { cir_set_error("cuTensorMapEncodeTiled (C) failed (%d)", (int)r); return CIR_ECUDA; }
+  return CIR_OK;
+}
+
 template <int BN, bool PAIR, bool LN>
-static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, const CUtensorMap& mw) {
+static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc) {
   using C = tc::Cfg<BN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -494,7 +535,7 @@ static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, c
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cir_prof_gemm_begin(ctx, 2.0 * (double)p.M * (double)p.N * (double)p.K * (double)p.batch);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_tcgen05_kernel<BN, PAIR, LN>, ma, mw, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_tcgen05_kernel<BN, PAIR, LN>, ma, mw, mc, p);
   cir_prof_gemm_end(ctx);
   if (e != cudaSuccess) { cir_set_error("tcgen05 GEMM launch failed: %s", cudaGetErrorString(e)); return CIR_ECUDA; }
   CIR_LAUNCH_CHECK(ctx);
@@ -547,7 +588,15 @@ int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a) {
   CUtensorMap ma, mw;
   CIR_TRY(cir_make_map_2d(ctx, &ma, a->A, a_rows, a->K, a->lda, tc::BM));
   CIR_TRY(cir_make_map_2d(ctx, &mw, a->W, w_rows, a->K, a->ldw, use_pair ? BN / 2 : BN));
-  if (use_pair) return p.ln_fuse ? launch_tc<256, true, true>(ctx, p, ma, mw) : launch_tc<256, true, false>(ctx, p, ma, mw);
-  if (use128) return launch_tc<128, false, false>(ctx, p, ma, mw);
-  return launch_tc<256, false, false>(ctx, p, ma, mw);
+  // bf16 outputs leave through TMA stores when the C layout is expressible as a tensor map (16 B aligned strides)
+  CUtensorMap mc = ma;
+  p.tma_store = 0;
+  if (ctx->gemm_tma_store && !a->c_f32 && !p.ln_fuse && (a->ldc % 8) == 0 && (a->N % 64) == 0 && ((uintptr_t)a->C & 15) == 0 &&
+      (a->batch == 1 || (a->c_bstride % 8) == 0) && a->M < (1ll << 31)) {
+    CIR_TRY(make_map_c(ctx, &mc, a->C, a->N, a->M, a->batch, a->ldc, a->c_bstride));
+    p.tma_store = 1;
+  }
+  if (use_pair) return p.ln_fuse ? launch_tc<256, true, true>(ctx, p, ma, mw, mc) : launch_tc<256, true, false>(ctx, p, ma, mw, mc);
+  if (use128) return launch_tc<128, false, false>(ctx, p, ma, mw, mc);
+  return launch_tc<256, false, false>(ctx, p, ma, mw, mc);
 }

@@ -68,6 +68,7 @@ extern "C" int cir_create(cir_ctx** out, int device, int dtype) {
   c->attn_impl = 0;
   c->gemm_pair = 1;
   c->prune_last = 1;
+  c->gemm_tma_store = 1;
   c->fuse_ln = 0;   // measured on B200: no gain over the separate HBM-bound LayerNorm kernels, so opt-in
   c->ln_gamma = nullptr; c->ln_beta = nullptr; c->ln_eps = 0.f;
   c->stream = 0;
@@ -120,6 +121,7 @@ extern "C" int cir_set_attention_impl(cir_ctx* ctx, int impl) {
 }
 extern "C" int cir_set_prune_last_layer(cir_ctx* ctx, int enable) { ctx->prune_last = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_set_fuse_layernorm(cir_ctx* ctx, int enable) { ctx->fuse_ln = enable ? 1 : 0; return CIR_OK; }
+extern "C" int cir_set_gemm_tma_store(cir_ctx* ctx, int enable) { ctx->gemm_tma_store = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_get_dtype(const cir_ctx* ctx) { return ctx->dtype; }
 extern "C" int64_t cir_launch_count(cir_ctx* ctx, int reset) {
   int64_t n = ctx->launches;

@@ -56,6 +56,10 @@ class Engine:
         """Stage II: layer 11 for the CLS rows only (default) or for all rows (cross-check)."""
         N.check(self._lib.cir_set_prune_last_layer(self.ctx, 1 if enable else 0))
 
+    def set_gemm_tma_store(self, enable: bool):
+        """bf16 GEMM outputs through TMA bulk tensor stores (default on) or per-lane 16 B stores."""
+        N.check(self._lib.cir_set_gemm_tma_store(self.ctx, 1 if enable else 0))
+
     def set_fuse_layernorm(self, enable: bool):
         """bf16 mode: LayerNorm inside the FFN2 GEMM epilogue (opt-in; default is the separate LayerNorm kernel)."""
         N.check(self._lib.cir_set_fuse_layernorm(self.ctx, 1 if enable else 0))

@@ -83,6 +83,7 @@ _SIGS = {
     "cir_set_attention_impl": (C.c_int, [vp, C.c_int]),
     "cir_set_prune_last_layer": (C.c_int, [vp, C.c_int]),
     "cir_set_fuse_layernorm": (C.c_int, [vp, C.c_int]),
+    "cir_set_gemm_tma_store": (C.c_int, [vp, C.c_int]),
     "cir_get_dtype": (C.c_int, [vp]),
     "cir_launch_count": (i64, [vp, C.c_int]),
     "cir_profile_gemm": (C.c_int, [vp, C.c_int]),

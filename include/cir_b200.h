@@ -71,6 +71,8 @@ int  cir_set_prune_last_layer(cir_ctx* ctx, int enable);
 /* bf16 mode: fuse LayerNorm into the long-K N=768 pair-tile GEMM epilogue (FFN2): statistics in the epilogue, in-place
  * normalisation pass from L2.  Default OFF: measured 53.7k vs 54.4k triplets/s for the separate LayerNorm kernels. */
 int  cir_set_fuse_layernorm(cir_ctx* ctx, int enable);
+/* 1 (default): bf16 GEMM outputs leave the tcgen05 epilogue through TMA bulk tensor stores; 0: per-lane 16 B stores. */
+int  cir_set_gemm_tma_store(cir_ctx* ctx, int enable);
 int  cir_get_dtype(const cir_ctx* ctx);
 /* number of kernel launches issued through this context since the last reset (bench.py's gpu_launches) */
 int64_t cir_launch_count(cir_ctx* ctx, int reset);

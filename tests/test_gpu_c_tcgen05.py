@@ -113,3 +113,24 @@ def test_tcgen05_shared_a_and_strided_rows(e16):
     N_.check(e16._lib.cir_gemm(e16.ctx, C.byref(g)))
     want = h[:, 0, :].double() @ W.double().T
     assert (out.double() - want).abs().max() < 2e-3
+
+
+def test_tma_store_epilogue_is_bit_identical(e16):
+    """bf16 outputs through cp.async.bulk.tensor stores vs. per-lane stores: same bytes, M tails clipped by the map,
+    rows of neighbouring batches untouched."""
+    for (M, N, K, b) in ((3300, 768, 768, 2), (130, 2304, 768, 2), (577 * 3, 3072, 768, 1), (31, 64, 64, 3)):
+        A = _rand(b, M, K, seed=1).bfloat16()
+        W = _rand(b, N, K, seed=2, scale=0.05).bfloat16()
+        bias = _rand(b, N, seed=3)
+        res16 = _rand(b, M, N, seed=4).bfloat16()
+        for kw in (dict(), dict(act=N_.ACT_GELU), dict(residual=res16)):
+            e16.set_gemm_impl(N_.GEMM_TCGEN05)
+            try:
+                e16.set_gemm_tma_store(True)
+                tma = e16.gemm(A, W, bias, **kw)
+                e16.set_gemm_tma_store(False)
+                lane = e16.gemm(A, W, bias, **kw)
+            finally:
+                e16.set_gemm_tma_store(True)
+                e16.set_gemm_impl(N_.GEMM_AUTO)
+            assert torch.equal(tma, lane), (M, N, K, b, kw)

@@ -30,6 +30,10 @@ def gemm_probe():
         bias = torch.randn(b, Nn, device="cuda")
         ms = timeit(lambda: e.gemm(A, W, bias, act=act))
         tf = 2.0 * M * Nn * K * b / ms / 1e9
+        e.set_gemm_tma_store(False)
+        ms_l = timeit(lambda: e.gemm(A, W, bias, act=act))
+        e.set_gemm_tma_store(True)
+        print(f"   (per-lane stores: {ms_l:.3f} ms {2.0 * M * Nn * K * b / ms_l / 1e9:.0f} TF/s)", flush=True)
         ms_t = timeit(lambda: torch.matmul(A, W.transpose(1, 2)))
         tf_t = 2.0 * M * Nn * K * b / ms_t / 1e9
         print(f"gemm M={M} N={Nn} K={K} batch={b} act={act}: {ms:.3f} ms {tf:.0f} TF/s | cuBLAS {ms_t:.3f} ms {tf_t:.0f} TF/s", flush=True)
