@@ -57,7 +57,8 @@ class BLIP_Retrieval(nn.Module):
 
     def img_txt_fusion(self, r_image_embeds, t_image_embeds, text, train=True, return_raw=False):
         """src/blip_stage1.py:67-92.  ``train=False, return_raw=True`` -> object with
-        ``.last_hidden_state`` [B,L,768] (z_t); ``train=False`` -> normalised [B,256]."""
+        ``.last_hidden_state`` [B,L,768] (z_t); ``train=False`` -> normalised [B,256]; ``train=True`` -> [B,Bt] logits
+        ``predicted @ t_image_embeds.T / temp`` (forward only)."""
         self._need_weights()
         e = self.engine
         ref = e.to_act(r_image_embeds)
@@ -65,9 +66,9 @@ class BLIP_Retrieval(nn.Module):
         ids, mask = tokenize(self.tokenizer, text, e.device)
         assert ids.shape[0] == B
         ar = torch.arange(B, dtype=torch.int32, device=e.device)
-        if train:
-            raise NotImplementedError("BLIP_Retrieval.img_txt_fusion(train=True) is the stage-I training loss path "
-                                      "(src/stage1_train.py), out of scope for the inference hot path")
+        if train:                                                # forward only: [B, Bt] in-batch logits (:88-91)
+            _, emb = e.stage1_encode(self._w, ref, ar, ids, mask, want_z=False, want_emb=True)
+            return e.stage1_logits(emb, t_image_embeds, self.temp)
         z, emb = e.stage1_encode(self._w, ref, ar, ids, mask, want_z=return_raw, want_emb=not return_raw)
         return EncoderOutput(last_hidden_state=z) if return_raw else emb
 

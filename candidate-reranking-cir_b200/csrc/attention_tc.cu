@@ -16,6 +16,7 @@
 //                 S_j = Q K_j^T  (A=Q smem, B=K_j smem, both K-major)
 //                 O  += P_j V_j  (A=P smem K-major, B=V_j smem MN-major)
 //   TMEM: S0, S1 (64 columns each) + O (64).  Scores and probabilities never touch HBM.
+#include <type_traits>
 #include "common.cuh"
 #include "tcgen05_ptx.cuh"
 
@@ -241,25 +242,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_cons
         rescale_o(o_addr, alpha);
       }
       if (j >= 2) mbar_wait(pvdone(pb), (uint32_t)(((j - 2) >> 1) & 1));     // P buffer pb: PV_{j-2} has read it
-      // ---- P = exp2(S*c - m) as bf16 into the swizzled A-operand tile (one 128 B row per thread); padded keys -> 0
+      // ---- P = exp2(S*c - m) as bf16 into the swizzled A-operand tile (one 128 B row per thread); padded keys -> 0.
+      //      Two instantiations: full chunks carry no per-element masking; the tail chunk only touches the
+      //      padded-to-16 keys the PV product reads.
       uint8_t* prow = smem + OFF_P + pb * P_BYTES + r * 128;
+      auto exp_store = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const int npad = (keys + 15) & ~15;
 #pragma unroll
-      for (int c = 0; c < 8; c++) {
-        float e[8];
+        for (int c = 0; c < 8; c++) {
+          if (!FULL && c * 8 >= npad) continue;
+          float e[8];
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const int i = c * 8 + q;
-          const float sv = __uint_as_float(i < 32 ? v0[i & 31] : v1[i & 31]);
-          e[q] = ex2_approx(fmaf(sv, sl2, -m));
-          if (!full_chunk && i >= keys) e[q] = 0.f;
+          for (int q = 0; q < 8; q++) {
+            const int i = c * 8 + q;
+            const float sv = __uint_as_float(i < 32 ? v0[i & 31] : v1[i & 31]);
+            e[q] = ex2_approx(fmaf(sv, sl2, -m));
+            if (!FULL && i >= keys) e[q] = 0.f;
+          }
+          l += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+          uint4 w;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+          for (int q = 0; q < 4; q++) h2[q] = __floats2bfloat162_rn(e[2 * q], e[2 * q + 1]);
+          *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = w;
         }
-        l += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-        uint4 w;
-        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-        for (int q = 0; q < 4; q++) h2[q] = __floats2bfloat162_rn(e[2 * q], e[2 * q + 1]);
-        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = w;
-      }
+      };
+      if (full_chunk) exp_store(std::true_type{}); else exp_store(std::false_type{});
       fence_proxy_async();                                   // generic-proxy P writes -> visible to the tensor core (async proxy)
       tcgen05_fence_before();
       __syncwarp();

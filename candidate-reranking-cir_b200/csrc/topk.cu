@@ -6,6 +6,7 @@
 //   cir_stage1_topk      fused 1 - q @ G^T tiles + running top-K       src/validate.py:57-58,202-203
 //   cir_topk_merge       merge of per-shard (dist, idx) lists after the NCCL all-gather
 //   cir_recall_counts    sum(labels[:, :k]) over sorted labels         src/validate_stage2.py:56-62,178-203
+#include <algorithm>
 #include "common.cuh"
 
 int cir_gemm_simt_f32(cir_ctx* ctx, const cir_gemm_args* a);   // gemm_simt.cu
@@ -219,6 +220,25 @@ extern "C" int cir_stage1_topk(cir_ctx* ctx, const float* q_emb, const float* g_
     topk_rows_kernel<<<(unsigned)Q, THREADS, 0, ctx->stream>>>(p);
     CIR_LAUNCH_CHECK(ctx);
   }
+  return CIR_OK;
+}
+
+__global__ void divide_rows_kernel(float* __restrict__ x, int64_t n, float d) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = x[i] / d;
+}
+
+extern "C" int cir_stage1_logits(cir_ctx* ctx, const float* q_emb, const float* t_emb, int64_t Q, int64_t G, float temp, float* logits) {
+  if (Q == 0 || G == 0) return CIR_OK;
+  CIR_CHECK_ARG(temp != 0.f, "stage1_logits: temp must be non-zero");
+  cir_gemm_args ga{};
+  ga.A = q_emb; ga.W = t_emb; ga.C = logits;
+  ga.M = Q; ga.N = G; ga.K = CIR_EMBED; ga.lda = CIR_EMBED; ga.ldw = CIR_EMBED; ga.ldc = G;
+  ga.batch = 1; ga.act = CIR_ACT_NONE; ga.c_f32 = 1;
+  CIR_TRY(cir_gemm_simt_f32(ctx, &ga));
+  const int64_t n = Q * G;
+  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->num_sms * 8);
+  divide_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(logits, n, temp);
+  CIR_LAUNCH_CHECK(ctx);
   return CIR_OK;
 }
 

@@ -359,6 +359,16 @@ class Engine:
                                           N.ptr(ti), N.ptr(ws), ws.numel()), "cir_stage1_topk")
         return td, ti
 
+    def stage1_logits(self, q_emb: torch.Tensor, t_emb: torch.Tensor, temp: float) -> torch.Tensor:
+        """q_emb [Q,256] @ t_emb [G,256]^T / temp in fp32 (src/blip_stage1.py:90-91)."""
+        q_emb = q_emb.to(self.device, torch.float32).contiguous()
+        t_emb = t_emb.to(self.device, torch.float32).contiguous()
+        out = torch.empty(q_emb.shape[0], t_emb.shape[0], dtype=torch.float32, device=self.device)
+        self._sync_stream()
+        N.check(self._lib.cir_stage1_logits(self.ctx, N.ptr(q_emb), N.ptr(t_emb), q_emb.shape[0], t_emb.shape[0], float(temp),
+                                            N.ptr(out)), "cir_stage1_logits")
+        return out
+
     def topk_merge(self, dist_in: torch.Tensor, idx_in: torch.Tensor):
         """dist_in/idx_in [P,Q,K] (per-shard sorted lists) -> merged (dist [Q,K], idx [Q,K])."""
         P, Q, K = dist_in.shape

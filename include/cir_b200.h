@@ -171,6 +171,10 @@ int cir_stage1_topk(cir_ctx* ctx, const float* q_emb, const float* g_emb, int64_
                     float* top_dist, int32_t* top_idx, void* workspace, size_t workspace_bytes);
 size_t cir_stage1_topk_workspace_bytes(int64_t Q, int64_t G, int64_t K);
 
+/* In-batch contrastive logits of the stage-I forward: logits[Q, G] = q_emb[Q,256] @ t_emb[G,256]^T / temp, all fp32.
+ * Replaces `predicted_features @ target_features.T / self.temp` (src/blip_stage1.py:90-91), forward only. */
+int cir_stage1_logits(cir_ctx* ctx, const float* q_emb, const float* t_emb, int64_t Q, int64_t G, float temp, float* logits);
+
 /* Merge P per-shard sorted lists pairs[p][Q][K] -> best K per query (ascending dist, ties ->
  * lowest global index).  The NCCL all-gather that assembles `dist_in/idx_in` is done by the host. */
 int cir_topk_merge(cir_ctx* ctx, const float* dist_in, const int32_t* idx_in, int64_t P, int64_t Q,

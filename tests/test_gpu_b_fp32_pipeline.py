@@ -52,6 +52,18 @@ def test_stage1_embeddings_and_topk(small):
     assert np.abs(td.cpu().numpy() - g["distances_topk"]).max() < 1e-6
 
 
+def test_stage1_in_batch_logits(small):
+    """BLIP_Retrieval.img_txt_fusion(train=True): predicted @ targets.T / temp (src/blip_stage1.py:88-91), forward only."""
+    g, m1, m2, images, tokens2 = small
+    tokens1, g_emb = m1.img_embed(images, return_pool_and_normalized=True)
+    tb = syn.TokenBatch(input_ids=torch.tensor(g["ids"]), attention_mask=torch.tensor(g["mask"]))
+    ref_idx = torch.tensor(g["ref_idx"])
+    logits = m1.img_txt_fusion(tokens1[ref_idx.cuda()], g_emb, tb, train=True)
+    want = g["q_emb"].astype(np.float64) @ g["g_emb"].astype(np.float64).T / m1.temp
+    assert logits.shape == (int(g["Q"]), g["g_emb"].shape[0]) and logits.dtype == torch.float32
+    assert np.abs(logits.cpu().numpy() - want).max() < 5e-4
+
+
 def test_z_t_and_stage2_scores_drop_in(small):
     g, m1, m2, images, tokens2 = small
     Q = int(g["Q"])

@@ -1,0 +1,36 @@
+// MUFU throughput probe: ex2.approx.f32 vs ex2.approx.f16x2 vs ex2.approx.ftz.bf16x2 (elements per clock per SM).
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+template <int MODE> __global__ void k(float* out, int iters) {
+  float a[8];
+  uint32_t h[8];
+  for (int i = 0; i < 8; i++) { a[i] = -0.001f * (threadIdx.x + i); h[i] = 0xB000B000u + threadIdx.x + i; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (MODE == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+      if (MODE == 1) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h[i]));
+      if (MODE == 2) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(h[i]));
+      if (MODE == 3) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[i]));
+      if (MODE == 4) asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(h[i]));
+    }
+  }
+  float s = 0; for (int i = 0; i < 8; i++) s += a[i] + __uint_as_float(h[i]);
+  if (s == 1234.5f) out[0] = s;
+}
+template <int MODE> void run(const char* name, int per) {
+  float* d; cudaMalloc(&d, 4);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int iters = 4096, blocks = 148 * 4, threads = 512;
+  k<MODE><<<blocks, threads>>>(d, 16);
+  cudaEventRecord(e0); k<MODE><<<blocks, threads>>>(d, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  double elems = (double)blocks * threads * iters * 8 * per;
+  printf("%-28s %.3f ms  %.2f Gelem/s  (%.1f elem/clk/SM at 1.9 GHz)\n", name, ms, elems / ms / 1e6, elems / ms / 1e6 * 1e9 / 148 / 1.9e9);
+}
+int main() {
+  run<0>("ex2.approx.ftz.f32", 1); run<1>("ex2.approx.f16x2", 2); run<2>("ex2.approx.ftz.bf16x2", 2);
+  run<3>("tanh.approx.f32", 1); run<4>("tanh.approx.bf16x2", 2);
+  return 0;
+}
