@@ -2,20 +2,28 @@
 // dual-stream encoder (32 text rows x 577 image keys per (triplet, stream, head),
 // src/nlvr_encoder.py:175-217) and the ViT self-attention (src/vit.py:74-82).
 //
-// One CTA = one 128-row query tile of one head; two CTAs are resident per SM.  A tile is (128/RB) batches
-// x RB rows that all attend the SAME K/V batch (candidate-major triplets: 4 triplets x 32 rows share one
-// candidate image), so the 128-row UMMA shape is filled although a triplet has only 32 query rows.
+// A work item = one 256-row query "double tile" of one head: two 128-row UMMA tiles A and B that attend the SAME
+// K/V batch, so every K/V chunk is fetched once per 256 query rows.  A double tile is (256/RB) batches x RB rows
+// (candidate-major triplets: 8 triplets x 32 rows share one candidate image), which fills the 128-row UMMA shape
+// although a triplet has only 32 query rows.  One persistent CTA per SM walks the items with a stride of the grid
+// size; rings, S/P buffers and mbarrier phases run on chunk counters that keep counting across items, so the next
+// item's Q/K/V loads and first S products overlap the current item's tail.
 //
-//   warps 0-3   softmax: thread r owns query row r == TMEM lane r.  Per 64-key chunk ONE tcgen05.ld sweep
-//               brings the row's scores into registers, row max -> exp2 -> bf16 P written to a 128B-swizzled
-//               shared-memory atom (the A operand of the PV product).  S and P are double-buffered, so the
-//               tensor core computes S_{j+1}, S_{j+2} while the softmax works on chunk j.  O accumulates in
-//               TMEM across chunks; the reference max moves lazily (only when the row max grew by more than
-//               2^8), so the O rescale (tcgen05.ld / tcgen05.st) is a rare path.
-//   warp 4      one elected thread: TMA loads of K/V chunks (3-deep rings) and all tcgen05.mma issue:
+//   warps 0-3   softmax of tile A, warps 4-7 softmax of tile B: thread r owns query row r == TMEM lane r.  Per
+//               64-key chunk ONE tcgen05.ld sweep brings the row's scores into registers, row max -> exp2 -> bf16 P
+//               written to a 128B-swizzled shared-memory atom (the A operand of the PV product).  S and P are
+//               double-buffered per tile, so the tensor core computes S_{j+1}, S_{j+2} while the softmax works on
+//               chunk j.  O accumulates in TMEM across chunks; the reference max moves lazily (only when the row
+//               max grew by more than 2^8), so the O rescale (tcgen05.ld / tcgen05.st) is a rare path.
+//   warp 8/9    one elected thread each: all tcgen05.mma issue of tile A / tile B:
 //                 S_j = Q K_j^T  (A=Q smem, B=K_j smem, both K-major)
 //                 O  += P_j V_j  (A=P smem K-major, B=V_j smem MN-major)
-//   TMEM: S0, S1 (64 columns each) + O (64).  Scores and probabilities never touch HBM.
+//               and the commits that hand the K / V ring stages back to the loader (2 arrivals per stage).
+//   warp 10     one elected thread: TMA loads of Q tiles (3-D map, double-buffered per tile) and of the K / V
+//               chunks into 6-deep rings -- deep enough that the L2 -> shared-memory latency under load
+//               (> 1 us) never reaches the MMA issue loop.
+//   TMEM: per tile S0, S1 (64 columns each) + O (64).  Scores and probabilities never touch HBM.
+#include <algorithm>
 #include <type_traits>
 #include "common.cuh"
 #include "tcgen05_ptx.cuh"
@@ -25,16 +33,21 @@ namespace fatc {
 using namespace tc;
 
 constexpr int KC = 64;                  // keys per chunk (one 128-byte swizzle atom of P per chunk)
-constexpr int KS = 3;                   // K / V ring depth
-constexpr int THREADS = 160;            // 4 softmax warps + 1 control warp
+constexpr int KS = 6;                   // K / V ring depth
+constexpr int THREADS = 352;            // 8 softmax warps + 2 MMA-issue warps + 1 loader warp
 constexpr int Q_BYTES = 128 * 128;      // 128 rows x 64 bf16
 constexpr int KV_BYTES = KC * 128;      // 64 keys x 64 bf16
 constexpr int P_BYTES = 128 * 128;      // [128 rows x 64 keys] bf16
-constexpr int OFF_Q = 0, OFF_K = Q_BYTES, OFF_V = OFF_K + KS * KV_BYTES, OFF_P = OFF_V + KS * KV_BYTES;
-constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
-constexpr int TMEM_COLS = 256;
-constexpr int S_COL = 0, O_COL = 128;   // S buffers at 0 and 64, O at 128
+constexpr int OFF_Q = 0;                               // [tile][item parity]
+constexpr int OFF_P = OFF_Q + 4 * Q_BYTES;             // [tile][chunk parity]
+constexpr int OFF_K = OFF_P + 4 * P_BYTES;
+constexpr int OFF_V = OFF_K + KS * KV_BYTES;
+constexpr int OFF_BAR = OFF_V + KS * KV_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 512;
+constexpr int TMEM_COLS = 512;
+constexpr int TILE_COLS = 256;          // TMEM columns per tile: S buffers at +0 and +64, O at +128
+constexpr int S_COL = 0, O_COL = 128;
+static_assert(SMEM_BYTES <= 232448, "attention_tc: shared memory budget");
 
 // instruction descriptor with an MN-major B operand (V is [key][dh], dh contiguous): bit 16
 __host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int m, int n) { return make_idesc_bf16(m, n) | (1u << 16); }
@@ -66,44 +79,73 @@ __device__ __noinline__ void rescale_o(uint32_t o_addr, float alpha) {
   tmem_st_wait();
 }
 
-__global__ void __launch_bounds__(THREADS, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, const cir_attn_args p,
-                    int ctas_per_batch) {
+struct Item { int batch0, nb, row0, kvrow0, h; };
+
+// work item w = head * ntiles + tile (tile fastest: CTAs running side by side share one candidate's K/V head slice in L2)
+__device__ __forceinline__ Item decode_item(const cir_attn_args& p, int w, int ntiles, int cpb) {
+  Item it;
+  it.h = w / ntiles;
+  const int t = w - it.h * ntiles;
+  if (p.tiles) {
+    const int4 d = __ldg(reinterpret_cast<const int4*>(p.tiles) + t);
+    it.batch0 = d.x; it.nb = d.y; it.row0 = d.z;
+  } else {
+    it.batch0 = t / cpb; it.nb = 1; it.row0 = (t - it.batch0 * cpb) * 256;
+  }
+  const int kvb = p.kv_index ? __ldg(p.kv_index + it.batch0) : it.batch0;
+  it.kvrow0 = kvb * p.Lk;
+  return it;
+}
+
+// the softmax warps only need the row geometry of an item: one load, consumed an item later
+__device__ __forceinline__ Item decode_rows(const cir_attn_args& p, int w, int ntiles, int cpb) {
+  Item it;
+  it.h = w / ntiles;
+  const int t = w - it.h * ntiles;
+  it.kvrow0 = 0;
+  if (p.tiles) {
+    const int4 d = __ldg(reinterpret_cast<const int4*>(p.tiles) + t);
+    it.batch0 = d.x; it.nb = d.y; it.row0 = d.z;
+  } else {
+    it.batch0 = t / cpb; it.nb = 1; it.row0 = (t - it.batch0 * cpb) * 256;
+  }
+  return it;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o, const cir_attn_args p,
+                    int cpb, int ntiles, int RB, int total) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.y;
-  // ---- CTA descriptor: 128 query rows r -> batch batch0 + r / RB, query row row0 + r % RB
-  int batch0, nb, row0, RB;
-  if (p.tiles) {
-    const int4 t = reinterpret_cast<const int4*>(p.tiles)[blockIdx.x];
-    batch0 = t.x; nb = t.y; row0 = t.z; RB = t.w;
-  } else {
-    batch0 = blockIdx.x / ctas_per_batch; nb = 1; row0 = (blockIdx.x % ctas_per_batch) * 128; RB = 128;
-  }
-  const int kvb = p.kv_index ? p.kv_index[batch0] : batch0;
   const int nch = (p.Lk + KC - 1) / KC;
+  const int n_my = (int)blockIdx.x < total ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total_g = n_my * nch;
 
-  // barriers (all indexed by chunk parity so a waiter is never more than one phase behind):
-  //   kfull[KS] vfull[KS] | sfull[2] pfull[2] pvdone[2] | qfull | tmem_ptr
+  // barriers: kfull[KS] vfull[KS] kempty[KS] vempty[KS] | per tile: sfull[2] pfull[2] pvdone[2] qfull[2] | tmem_ptr
+  // (S / P / pvdone indexed by chunk parity, Q by item parity, so a waiter is never more than one phase behind)
   const uint32_t bar = sbase + OFF_BAR;
   auto kfull = [&](int s) { return bar + 8u * s; };
   auto vfull = [&](int s) { return bar + 8u * (KS + s); };
-  auto sfull = [&](int b) { return bar + 8u * (2 * KS + b); };
-  auto pfull = [&](int b) { return bar + 8u * (2 * KS + 2 + b); };
-  auto pvdone = [&](int b) { return bar + 8u * (2 * KS + 4 + b); };
-  const uint32_t qfull = bar + 8u * (2 * KS + 6);
-  const uint32_t tmem_ptr_smem = qfull + 8;
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (2 * KS + 6) + 8);
+  auto kempty = [&](int s) { return bar + 8u * (2 * KS + s); };
+  auto vempty = [&](int s) { return bar + 8u * (3 * KS + s); };
+  auto sfull = [&](int t, int b) { return bar + 8u * (4 * KS + t * 8 + b); };
+  auto pfull = [&](int t, int b) { return bar + 8u * (4 * KS + t * 8 + 2 + b); };
+  auto pvdone = [&](int t, int b) { return bar + 8u * (4 * KS + t * 8 + 4 + b); };
+  auto qfull = [&](int t, int b) { return bar + 8u * (4 * KS + t * 8 + 6 + b); };
+  const uint32_t tmem_ptr_smem = bar + 8u * (4 * KS + 16);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (4 * KS + 16));
 
   if ((sbase & 1023u) != 0) { if (tid == 0) printf("cir: attention_tc smem misaligned\n"); __trap(); }
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
+      tma_prefetch_desc(&map_q);
       tma_prefetch_desc(&map_k);
       tma_prefetch_desc(&map_v);
-      for (int s = 0; s < KS; s++) { mbar_init(kfull(s), 1); mbar_init(vfull(s), 1); }
-      for (int b = 0; b < 2; b++) { mbar_init(sfull(b), 1); mbar_init(pfull(b), 4); mbar_init(pvdone(b), 1); }
-      mbar_init(qfull, 4);
+      for (int s = 0; s < KS; s++) { mbar_init(kfull(s), 1); mbar_init(vfull(s), 1); mbar_init(kempty(s), 2); mbar_init(vempty(s), 2); }
+      for (int t = 0; t < 2; t++)
+        for (int b = 0; b < 2; b++) { mbar_init(sfull(t, b), 1); mbar_init(pfull(t, b), 4); mbar_init(pvdone(t, b), 1); mbar_init(qfull(t, b), 1); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -114,195 +156,257 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
-  if (warp == 4) {
-    // ===================== control: TMA + MMA issue =====================
-    if (elect_one()) {
-      const int32_t krow0 = kvb * p.Lk;
-      const int32_t col = h * 64;
-      auto load_k = [&](int j) {
-        const int s = j % KS;
+  auto n_pad_of = [&](int j) {
+    const int keys = (p.Lk - j * KC) < KC ? (p.Lk - j * KC) : KC;
+    return (keys + 15) & ~15;                                // UMMA N (multiple of 16); padded keys are masked in the softmax
+  };
+
+  if (warp == 10) {
+    // ===================== loader: TMA for Q tiles and the K / V rings =====================
+    if (elect_one() && total_g > 0) {
+      auto dec = [&](int i) { return i < n_my ? decode_item(p, (int)blockIdx.x + i * (int)gridDim.x, ntiles, cpb) : Item{}; };
+      // items i_cur .. i_cur+2 decoded ahead: the two dependent global loads of a decode never stall the ring
+      Item it0 = dec(0), it1 = dec(1), it2 = dec(2);
+      int i_cur = 0;
+      auto item_at = [&](int i) -> Item { return i == i_cur ? it0 : (i == i_cur + 1 ? it1 : (i == i_cur + 2 ? it2 : dec(i))); };
+      const int rbq = RB < 128 ? RB : 128;                   // rows per batch inside one 128-row tile
+      auto issue_q = [&](int i) {                           // both tiles of item i; rows / batches out of bounds arrive as zeros
+        const Item it = item_at(i);
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+          mbar_expect_tx(qfull(t, i & 1), Q_BYTES);
+          const int row = RB > 128 ? it.row0 + t * 128 : it.row0;
+          const int bat = RB > 128 ? it.batch0 : it.batch0 + t * (128 / rbq);
+          tma_load_3d(sbase + OFF_Q + (t * 2 + (i & 1)) * Q_BYTES, &map_q, qfull(t, i & 1), it.h * 64, row, bat);
+        }
+      };
+      int q_next = 0;
+      for (; q_next < 2 && q_next < n_my; q_next++) issue_q(q_next);
+      int i = 0, j = 0;
+      for (int g = 0; g < total_g; g++) {
+        const int s = g % KS;
+        const uint32_t ph = (uint32_t)((g / KS) & 1);
+        const Item it = item_at(i);
+        if (g >= KS) mbar_wait(kempty(s), ph ^ 1u);          // both tiles' S_{g-KS} retired
         mbar_expect_tx(kfull(s), KV_BYTES);
-        tma_load_2d(sbase + OFF_K + s * KV_BYTES, &map_k, kfull(s), col, krow0 + j * KC);
-      };
-      auto load_v = [&](int j) {
-        const int s = j % KS;
+        tma_load_2d(sbase + OFF_K + s * KV_BYTES, &map_k, kfull(s), it.h * 64, it.kvrow0 + j * KC);
+        if (g >= KS) mbar_wait(vempty(s), ph ^ 1u);          // both tiles' PV_{g-KS} retired
         mbar_expect_tx(vfull(s), KV_BYTES);
-        tma_load_2d(sbase + OFF_V + s * KV_BYTES, &map_v, vfull(s), col, krow0 + j * KC);
-      };
-      auto n_pad_of = [&](int j) {
-        const int keys = (p.Lk - j * KC) < KC ? (p.Lk - j * KC) : KC;
-        return (keys + 15) & ~15;                            // UMMA N (multiple of 16); padded keys are masked in the softmax
-      };
-      const uint64_t qdesc = make_smem_desc_sw128(sbase + OFF_Q);
-      auto issue_s = [&](int j) {                           // S[j&1] = Q K_j^T
-        mbar_wait(kfull(j % KS), (uint32_t)((j / KS) & 1));
+        tma_load_2d(sbase + OFF_V + s * KV_BYTES, &map_v, vfull(s), it.h * 64, it.kvrow0 + j * KC);
+        // Q buffers of item q_next were last read by the S products of item q_next-2, whose last chunk is
+        // (q_next-1)*nch - 1: its kempty has been observed once this loop has passed g = that + KS
+        while (q_next < n_my && (q_next - 1) * nch - 1 + KS <= g) issue_q(q_next++);
+        if (++j == nch) { j = 0; i++; i_cur = i; it0 = it1; it1 = it2; it2 = dec(i + 2); }
+      }
+      while (q_next < n_my) {                                // only reachable when nch < KS / 2: the ring never wrapped that far
+        const int need = (q_next - 1) * nch - 1;             // chunk whose S products must have retired
+        mbar_wait(kempty(need % KS), (uint32_t)((need / KS) & 1));
+        issue_q(q_next++);
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== MMA issue for tile t =====================
+    const int t = warp - 8;
+    if (elect_one() && total_g > 0) {
+      const uint32_t tm = tmem_base + t * TILE_COLS;
+      auto issue_s = [&](int g) {                           // S[g&1] = Q_i K_j^T
+        const int i = g / nch, j = g - i * nch, s = g % KS;
+        if (j == 0) mbar_wait(qfull(t, i & 1), (uint32_t)((i >> 1) & 1));
+        mbar_wait(kfull(s), (uint32_t)((g / KS) & 1));
         tcgen05_fence_after();
-        const uint64_t kdesc = make_smem_desc_sw128(sbase + OFF_K + (j % KS) * KV_BYTES);
+        const uint64_t qdesc = make_smem_desc_sw128(sbase + OFF_Q + (t * 2 + (i & 1)) * Q_BYTES);
+        const uint64_t kdesc = make_smem_desc_sw128(sbase + OFF_K + s * KV_BYTES);
         const uint32_t idesc = make_idesc_bf16(128, n_pad_of(j));
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          umma_bf16(tmem_base + S_COL + (j & 1) * 64, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc, (uint32_t)(k != 0));
-        umma_commit(sfull(j & 1));
+          umma_bf16(tm + S_COL + (g & 1) * 64, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc, (uint32_t)(k != 0));
+        umma_commit(sfull(t, g & 1));
+        umma_commit(kempty(s));                              // this tile is done with K stage s
       };
-      const int pre = nch < KS ? nch : KS;
-      for (int j = 0; j < pre; j++) { load_k(j); load_v(j); }
-      mbar_wait(qfull, 0);                                  // Q tile written (generic proxy) + proxy fence by the softmax warps
       issue_s(0);
-      if (nch > 1) issue_s(1);
-      for (int j = 0; j < nch; j++) {
-        mbar_wait(pfull(j & 1), (uint32_t)((j >> 1) & 1));   // P_j in shared memory, S_j consumed, O rescaled if needed
-        mbar_wait(vfull(j % KS), (uint32_t)((j / KS) & 1));
+      if (total_g > 1) issue_s(1);
+      int j = 0;
+      for (int g = 0; g < total_g; g++) {
+        const int s = g % KS;
+        mbar_wait(pfull(t, g & 1), (uint32_t)((g >> 1) & 1));    // P_g in shared memory, S_g consumed, O rescaled if needed
+        mbar_wait(vfull(s), (uint32_t)((g / KS) & 1));
         tcgen05_fence_after();
-        {                                                    // O (+)= P_j V_j, accumulating in TMEM across chunks
+        {                                                    // O (+)= P_g V_g, accumulating in TMEM across the item's chunks
           const uint32_t idesc = make_idesc_bf16_bmn(128, 64);
           const int ksteps = n_pad_of(j) >> 4;
           for (int k = 0; k < ksteps; k++) {
-            const uint64_t pdesc = make_smem_desc_sw128(sbase + OFF_P + (j & 1) * P_BYTES) + (uint64_t)(k * 2);    // +32 B per 16 keys
-            const uint64_t vdesc = make_smem_desc_sw128(sbase + OFF_V + (j % KS) * KV_BYTES + k * 2048);         // 16 key rows x 128 B
-            umma_bf16(tmem_base + O_COL, pdesc, vdesc, idesc, (uint32_t)((j | k) != 0));
+            const uint64_t pdesc = make_smem_desc_sw128(sbase + OFF_P + (t * 2 + (g & 1)) * P_BYTES) + (uint64_t)(k * 2);   // +32 B per 16 keys
+            const uint64_t vdesc = make_smem_desc_sw128(sbase + OFF_V + s * KV_BYTES + k * 2048);                          // 16 key rows x 128 B
+            umma_bf16(tm + O_COL, pdesc, vdesc, idesc, (uint32_t)((j | k) != 0));
           }
-          umma_commit(pvdone(j & 1));
+          umma_commit(pvdone(t, g & 1));
+          umma_commit(vempty(s));                            // this tile is done with V stage s
         }
-        if (j + 2 < nch) issue_s(j + 2);                     // S buffer j&1 was drained before pfull(j)
-        if (j + KS < nch) load_k(j + KS);                    // S_j retired long ago -> K_j's stage is free
-        if (j >= 1 && j - 1 + KS < nch) {                    // V_{j-1}'s stage once PV_{j-1} retired
-          mbar_wait(pvdone((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
-          load_v(j - 1 + KS);
-        }
+        if (g + 2 < total_g) issue_s(g + 2);                 // S buffer g&1 was drained before pfull(g)
+        if (++j == nch) j = 0;
       }
     }
   } else {
     // ===================== softmax warps: thread = query row = TMEM lane =====================
-    const int r = tid;                                       // 0..127
-    const int bi = r / RB, qi = row0 + r % RB;
-    const bool valid = bi < nb && qi < p.Lq;
-    const int b = batch0 + (bi < nb ? bi : 0);
-    // ---- Q row -> swizzled shared memory (K-major SWIZZLE_128B: 16 B piece c of row r lives at c ^ (r & 7))
-    {
-      const uint4* qsrc = reinterpret_cast<const uint4*>((const bf16*)p.q + (int64_t)b * p.q_bs + (int64_t)qi * p.q_rs + h * 64);
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        const uint4 v = valid ? qsrc[c] : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(smem + OFF_Q + r * 128 + ((c ^ (r & 7)) << 4)) = v;
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(qfull);
-    }
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int t = warp >> 2;                                 // tile A (warps 0-3) or B (warps 4-7)
+    const int r = tid & 127;                                 // row inside the tile == TMEM lane
+    const int rr = t * 128 + r;                              // row inside the double tile
+    const uint32_t lane_addr = tmem_base + t * TILE_COLS + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t o_addr = lane_addr + O_COL;
     const float sl2 = p.scale * 1.4426950408889634f;
-    float m = -INFINITY, l = 0.f;                            // m: lazily updated reference max (scaled log2 domain)
-    for (int j = 0; j < nch; j++) {
-      const int pb = j & 1;
-      const int keys = (p.Lk - j * KC) < KC ? (p.Lk - j * KC) : KC;
-      const bool full_chunk = keys == KC;
-      const bool two = keys > 32;                            // second 32-column piece needed?
-      mbar_wait(sfull(pb), (uint32_t)((j >> 1) & 1));
-      tcgen05_fence_after();
-      // ---- the row's 64 scores -> registers in one sweep
-      uint32_t v0[32], v1[32];
-      __syncwarp();
-      tmem_ld_32x32b_x32(lane_addr + S_COL + pb * 64, v0);
-      if (two) tmem_ld_32x32b_x32(lane_addr + S_COL + pb * 64 + 32, v1);
-      tmem_ld_wait();
-      // ---- row max of the chunk
-      float cmax = -INFINITY;
-      if (full_chunk) {                                      // four independent FMNMX3 chains (8 deep instead of 32)
-        float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          c0 = max3(c0, __uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
-          c1 = max3(c1, __uint_as_float(v0[16 + i]), __uint_as_float(v0[17 + i]));
-          c2 = max3(c2, __uint_as_float(v1[i]), __uint_as_float(v1[i + 1]));
-          c3 = max3(c3, __uint_as_float(v1[16 + i]), __uint_as_float(v1[17 + i]));
-        }
-        cmax = fmaxf(max3(c0, c1, c2), c3);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; i++) if (i < keys) cmax = fmaxf(cmax, __uint_as_float(v0[i]));
-        if (two) {
-#pragma unroll
-          for (int i = 0; i < 32; i++) if (32 + i < keys) cmax = fmaxf(cmax, __uint_as_float(v1[i]));
-        }
-      }
-      cmax *= sl2;                                           // scale > 0: max commutes with the scaling
-      // ---- lazy reference max: move it only when the row max grew by more than 2^8; the (rare) move rescales
-      //      l and the O accumulator in TMEM.  Otherwise exp2(s - m) <= 256: harmless in fp32 / bf16.
-      const bool grow = cmax > m + 8.0f;
-      if (j == 0) {
-        m = cmax;
-      } else if (__any_sync(0xffffffffu, grow)) {
-        mbar_wait(pvdone((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));      // every PV issued so far has retired
+    // Warp w of tile A and warp w of tile B sit on the same scheduler and share its MUFU.  Left alone they fall into
+    // lock-step: both exp2 phases collide, and the unit idles while both do max / waits / tcgen05.ld.  Two named
+    // barriers per warp pair make the exp2 phases strictly alternate, so one tile's exp2 runs under the other's
+    // non-MUFU work.
+    const int wq = warp & 3;
+    auto turn_wait = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(t == 0 ? 5 + wq : 1 + wq) : "memory"); };
+    auto turn_pass = [&]() { asm volatile("bar.arrive %0, 64;" ::"r"(t == 0 ? 1 + wq : 5 + wq) : "memory"); };
+    int g = 0;
+    Item nxt = n_my > 0 ? decode_rows(p, (int)blockIdx.x, ntiles, cpb) : Item{};
+    bool o_pending = false;                                  // a TMA store of this warp may still be reading its P slice
+    for (int it_i = 0; it_i < n_my; it_i++) {
+      const Item it = nxt;
+      if (it_i + 1 < n_my) nxt = decode_rows(p, (int)blockIdx.x + (it_i + 1) * (int)gridDim.x, ntiles, cpb);   // off the critical path
+      const int bi = rr / RB, qi = it.row0 + rr % RB;
+      const bool valid = bi < it.nb && qi < p.Lq;
+      const int b = it.batch0 + (bi < it.nb ? bi : 0);
+      float m = -INFINITY, l = 0.f;                          // m: lazily updated reference max (scaled log2 domain)
+      for (int j = 0; j < nch; j++, g++) {
+        const int pb = g & 1;
+        const int keys = (p.Lk - j * KC) < KC ? (p.Lk - j * KC) : KC;
+        const bool full_chunk = keys == KC;
+        const bool two = keys > 32;                          // second 32-column piece needed?
+        mbar_wait(sfull(t, pb), (uint32_t)((g >> 1) & 1));
         tcgen05_fence_after();
-        const float m_new = grow ? cmax : m;
-        const float alpha = ex2_approx(m - m_new);           // 1 for rows that keep their reference
-        l *= alpha;
-        m = m_new;
-        rescale_o(o_addr, alpha);
-      }
-      if (j >= 2) mbar_wait(pvdone(pb), (uint32_t)(((j - 2) >> 1) & 1));     // P buffer pb: PV_{j-2} has read it
-      // ---- P = exp2(S*c - m) as bf16 into the swizzled A-operand tile (one 128 B row per thread); padded keys -> 0.
-      //      Two instantiations: full chunks carry no per-element masking; the tail chunk only touches the
-      //      padded-to-16 keys the PV product reads.
-      uint8_t* prow = smem + OFF_P + pb * P_BYTES + r * 128;
-      auto exp_store = [&](auto full_tag) {
-        constexpr bool FULL = decltype(full_tag)::value;
-        const int npad = (keys + 15) & ~15;
+        // ---- the row's 64 scores -> registers in one sweep
+        uint32_t v0[32], v1[32];
+        __syncwarp();
+        tmem_ld_32x32b_x32(lane_addr + S_COL + pb * 64, v0);
+        if (two) tmem_ld_32x32b_x32(lane_addr + S_COL + pb * 64 + 32, v1);
+        tmem_ld_wait();
+        // ---- row max of the chunk
+        float cmax = -INFINITY;
+        if (full_chunk) {                                    // four independent FMNMX3 chains (8 deep instead of 32)
+          float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-          if (!FULL && c * 8 >= npad) continue;
-          float e[8];
-#pragma unroll
-          for (int q = 0; q < 8; q++) {
-            const int i = c * 8 + q;
-            const float sv = __uint_as_float(i < 32 ? v0[i & 31] : v1[i & 31]);
-            e[q] = ex2_approx(fmaf(sv, sl2, -m));
-            if (!FULL && i >= keys) e[q] = 0.f;
+          for (int x = 0; x < 16; x += 2) {
+            c0 = max3(c0, __uint_as_float(v0[x]), __uint_as_float(v0[x + 1]));
+            c1 = max3(c1, __uint_as_float(v0[16 + x]), __uint_as_float(v0[17 + x]));
+            c2 = max3(c2, __uint_as_float(v1[x]), __uint_as_float(v1[x + 1]));
+            c3 = max3(c3, __uint_as_float(v1[16 + x]), __uint_as_float(v1[17 + x]));
           }
-          l += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+          cmax = fmaxf(max3(c0, c1, c2), c3);
+        } else {
+#pragma unroll
+          for (int x = 0; x < 32; x++) if (x < keys) cmax = fmaxf(cmax, __uint_as_float(v0[x]));
+          if (two) {
+#pragma unroll
+            for (int x = 0; x < 32; x++) if (32 + x < keys) cmax = fmaxf(cmax, __uint_as_float(v1[x]));
+          }
+        }
+        cmax *= sl2;                                         // scale > 0: max commutes with the scaling
+        // ---- lazy reference max: move it only when the row max grew by more than 2^8; the (rare) move rescales
+        //      l and the O accumulator in TMEM.  Otherwise exp2(s - m) <= 256: harmless in fp32 / bf16.
+        const bool grow = cmax > m + 8.0f;
+        if (j == 0) {
+          m = cmax;
+        } else if (__any_sync(0xffffffffu, grow)) {
+          mbar_wait(pvdone(t, (g - 1) & 1), (uint32_t)(((g - 1) >> 1) & 1));   // every PV issued so far has retired
+          tcgen05_fence_after();
+          const float m_new = grow ? cmax : m;
+          const float alpha = ex2_approx(m - m_new);         // 1 for rows that keep their reference
+          l *= alpha;
+          m = m_new;
+          rescale_o(o_addr, alpha);
+        }
+        if (g >= 2) mbar_wait(pvdone(t, pb), (uint32_t)(((g - 2) >> 1) & 1));  // P buffer pb: PV_{g-2} has read it
+        // ---- P = exp2(S*c - m) as bf16 into the swizzled A-operand tile (one 128 B row per thread); padded keys -> 0.
+        //      Two instantiations: full chunks carry no per-element masking; the tail chunk only touches the
+        //      padded-to-16 keys the PV product reads.
+        if (o_pending) {                                     // the previous item's O tile left through this warp's P slice
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+          o_pending = false;
+        }
+        uint8_t* prow = smem + OFF_P + (t * 2 + pb) * P_BYTES + r * 128;
+        auto exp_store = [&](auto full_tag) {
+          constexpr bool FULL = decltype(full_tag)::value;
+          const int npad = (keys + 15) & ~15;
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            if (!FULL && c * 8 >= npad) continue;
+            float e[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const int x = c * 8 + q;
+              const float sv = __uint_as_float(x < 32 ? v0[x & 31] : v1[x & 31]);
+              e[q] = ex2_approx(fmaf(sv, sl2, -m));
+              if (!FULL && x >= keys) e[q] = 0.f;
+            }
+            l += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+            uint4 w;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+            for (int q = 0; q < 4; q++) h2[q] = __floats2bfloat162_rn(e[2 * q], e[2 * q + 1]);
+            *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = w;
+          }
+        };
+        if (t == 1 || g > 0) turn_wait();
+        if (full_chunk) exp_store(std::true_type{}); else exp_store(std::false_type{});
+        turn_pass();
+        fence_proxy_async();                                 // generic-proxy P writes -> visible to the tensor core (async proxy)
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pfull(t, pb));
+      }
+      // ---- O, normalise, store.  The next item's first PV (accumulate = 0) is issued only after these warps signal
+      //      its pfull, i.e. after this read of O: one O accumulator per tile suffices.
+      mbar_wait(pvdone(t, (g - 1) & 1), (uint32_t)(((g - 1) >> 1) & 1));
+      tcgen05_fence_after();
+      const float inv = 1.0f / l;
+      // A warp's 32 rows are one batch when RB >= 32: the tile then leaves as ONE TMA store (rows >= Lq clipped by the
+      // map) staged in this warp's slice of the P buffer that PV_{g-1} has finished reading.  Otherwise per-row stores.
+      const int rr0 = t * 128 + (warp & 3) * 32;
+      const bool warp_tma = RB >= 32 && (rr0 / RB) < it.nb;
+      const bool warp_skip = RB >= 32 && !warp_tma;          // the warp's batch does not exist in this tile
+      uint8_t* stage = smem + OFF_P + (t * 2 + ((g - 1) & 1)) * P_BYTES + (warp & 3) * 4096 + lane * 128;
+      uint4* dst = reinterpret_cast<uint4*>((bf16*)p.o + (int64_t)b * p.o_bs + (int64_t)qi * p.o_rs + it.h * 64);
+#pragma unroll
+      for (int hh = 0; hh < 2; hh++) {
+        uint32_t ov[32];
+        __syncwarp();
+        tmem_ld_32x32b_x32(o_addr + hh * 32, ov);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
           uint4 w;
           __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w);
 #pragma unroll
-          for (int q = 0; q < 4; q++) h2[q] = __floats2bfloat162_rn(e[2 * q], e[2 * q + 1]);
-          *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = w;
+          for (int q = 0; q < 4; q++)
+            h2[q] = __floats2bfloat162_rn(__uint_as_float(ov[c * 8 + 2 * q]) * inv, __uint_as_float(ov[c * 8 + 2 * q + 1]) * inv);
+          if (warp_tma) *reinterpret_cast<uint4*>(stage + (((hh * 4 + c) ^ (lane & 7)) << 4)) = w;
+          else if (valid && !warp_skip) dst[hh * 4 + c] = w;
         }
-      };
-      if (full_chunk) exp_store(std::true_type{}); else exp_store(std::false_type{});
-      fence_proxy_async();                                   // generic-proxy P writes -> visible to the tensor core (async proxy)
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pfull(pb));
-    }
-    // ---- O, normalise, store
-    mbar_wait(pvdone((nch - 1) & 1), (uint32_t)(((nch - 1) >> 1) & 1));
-    tcgen05_fence_after();
-    float o[64];
-#pragma unroll
-    for (int hh = 0; hh < 2; hh++) {
-      uint32_t ov[32];
-      __syncwarp();
-      tmem_ld_32x32b_x32(o_addr + hh * 32, ov);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; i++) o[hh * 32 + i] = __uint_as_float(ov[i]);
-    }
-    if (valid) {
-      const float inv = 1.0f / l;
-      uint4* dst = reinterpret_cast<uint4*>((bf16*)p.o + (int64_t)b * p.o_bs + (int64_t)qi * p.o_rs + h * 64);
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        uint4 w;
-        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-        for (int q = 0; q < 4; q++) h2[q] = __floats2bfloat162_rn(o[c * 8 + 2 * q] * inv, o[c * 8 + 2 * q + 1] * inv);
-        dst[c] = w;
       }
+      if (warp_tma) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const int bw = it.batch0 + rr0 / RB, qw = it.row0 + rr0 % RB;
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                       ::"l"(&map_o), "r"(smem_u32(stage)), "r"(it.h * 64), "r"(qw), "r"(bw) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        o_pending = true;
+      }
+      tcgen05_fence_before();                                // O reads ordered before the pfull arrive that releases the next PV
     }
   }
+  if (warp < 4 && total_g > 0) asm volatile("bar.sync %0, 64;" ::"r"(5 + (warp & 3)) : "memory");   // tile B's last turn_pass
+  if (warp < 8 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // outstanding O stores
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tcgen05_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
@@ -320,7 +424,13 @@ int cir_attention_tc(cir_ctx* ctx, const cir_attn_args* a) {
   if (!a->tiles && a->Lq <= 64 && a->B > 1) return CIR_EUNSUPPORTED;      // unshared short queries would waste most of every tile
   const int64_t kv_rows = (int64_t)a->kv_batches * a->Lk;
   if (kv_rows >= (1ll << 31)) return CIR_EUNSUPPORTED;
-  CUtensorMap mk, mv;
+  // double-tile geometry: RB rows per batch (schedule.build_attn_tiles: smallest power of two >= Lq, at most 256)
+  int RB = 256;
+  if (a->tiles) { RB = 1; while (RB < a->Lq && RB < 256) RB <<= 1; }
+  const int rbq = RB < 128 ? RB : 128;
+  CUtensorMap mq, mk, mv, mo;
+  CIR_TRY(cir_make_map_3d(ctx, &mq, a->q, (int64_t)a->H * 64, a->Lq, a->B, a->q_rs, a->q_bs, 64, rbq, 128 / rbq));
+  CIR_TRY(cir_make_map_3d(ctx, &mo, a->o, (int64_t)a->H * 64, a->Lq, a->B, a->o_rs, a->o_bs, 64, 32, 1));
   CIR_TRY(cir_make_map_2d(ctx, &mk, a->k, kv_rows, (int64_t)a->H * 64, a->k_rs, fatc::KC));
   CIR_TRY(cir_make_map_2d(ctx, &mv, a->v, kv_rows, (int64_t)a->H * 64, a->v_rs, fatc::KC));
   static bool attr_set = false;
@@ -328,10 +438,13 @@ int cir_attention_tc(cir_ctx* ctx, const cir_attn_args* a) {
     CIR_CUDA(cudaFuncSetAttribute(fatc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fatc::SMEM_BYTES));
     attr_set = true;
   }
-  const int cpb = (a->Lq + 127) / 128;
-  const unsigned gx = a->tiles ? (unsigned)a->num_tiles : (unsigned)(a->B * cpb);
-  if (gx == 0) return CIR_OK;
-  fatc::attention_tc_kernel<<<dim3(gx, (unsigned)a->H), fatc::THREADS, fatc::SMEM_BYTES, ctx->stream>>>(mk, mv, *a, cpb);
+  const int cpb = (a->Lq + 255) / 256;
+  const int64_t ntiles = a->tiles ? (int64_t)a->num_tiles : (int64_t)a->B * cpb;
+  const int64_t total = ntiles * a->H;
+  if (total == 0) return CIR_OK;
+  if (total >= (1ll << 31)) return CIR_EUNSUPPORTED;
+  const unsigned gx = (unsigned)std::min<int64_t>(total, (int64_t)ctx->num_sms);      // persistent: one CTA per SM
+  fatc::attention_tc_kernel<<<gx, fatc::THREADS, fatc::SMEM_BYTES, ctx->stream>>>(mq, mk, mv, mo, *a, cpb, (int)ntiles, RB, (int)total);
   CIR_LAUNCH_CHECK(ctx);
   return CIR_OK;
 }

@@ -97,6 +97,9 @@ int cir_gemm_simt(cir_ctx* ctx, const cir_gemm_args* a);
 int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a);
 // 2-D bf16 tensor map over a [rows, K] row-major matrix (row stride ld elements), box [box_rows, 64], SWIZZLE_128B
 int cir_make_map_2d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows);
+// 3-D bf16 map, SWIZZLE_128B: dims (d0 contiguous, d1 stride s1, d2 stride s2; strides in elements), box (b0 <= 64, b1, b2)
+int cir_make_map_3d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1, int64_t s2,
+                    int b0, int b1, int b2);
 int cir_attention_tc(cir_ctx* ctx, const cir_attn_args* a);
 // true when cir_gemm_tcgen05 would use the cta_group::2 pair tile for this shape (the fused LayerNorm needs it)
 bool cir_gemm_uses_pair(const cir_ctx* ctx, int64_t M, int64_t N, int batch);    // attention_tc.cu; CIR_EUNSUPPORTED -> caller falls back

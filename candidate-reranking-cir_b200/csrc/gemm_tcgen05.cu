@@ -498,18 +498,27 @@ int cir_make_map_2d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t ro
   return CIR_OK;
 }
 
-// 3-D bf16 tensor map over C: (N, M, batch), box [1, 32 rows, 64 cols], SWIZZLE_128B -- one epilogue warp's staging tile
-static int make_map_c(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t N, int64_t M, int64_t batch, int64_t ldc, int64_t c_bstride) {
+int cir_make_map_3d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1, int64_t s2,
+                    int b0, int b1, int b2) {
   PFN_encodeTiled enc;
   CIR_TRY(get_encode_fn(ctx, &enc));
-  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)batch};
-  cuuint64_t strides[2] = {(cuuint64_t)ldc * 2, (cuuint64_t)(batch > 1 ? c_bstride : M * ldc) * 2};
-  cuuint32_t box[3] = {64, 32, 1};
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)s1 * 2, (cuuint64_t)(d2 > 1 ? s2 : d1 * s1) * 2};
+  cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { cir_set_error("cuTensorMapEncodeTiled (C) failed (%d)", (int)r); return CIR_ECUDA; }
+  if (r != CUDA_SUCCESS) {
+    cir_set_error("cuTensorMapEncodeTiled (3-D) failed (%d): base=%p dims=(%lld,%lld,%lld) strides=(%lld,%lld) box=(%d,%d,%d)", (int)r, base,
+                  (long long)d0, (long long)d1, (long long)d2, (long long)s1, (long long)s2, b0, b1, b2);
+    return CIR_ECUDA;
+  }
   return CIR_OK;
+}
+
+// C as (N, M, batch) with box [64 cols, 32 rows, 1]: one epilogue warp's staging tile
+static int make_map_c(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t N, int64_t M, int64_t batch, int64_t ldc, int64_t c_bstride) {
+  return cir_make_map_3d(ctx, map, base, N, M, batch, ldc, c_bstride, 64, 32, 1);
 }
 
 template <int BN, bool PAIR, bool LN>

@@ -107,28 +107,31 @@ def build_attn_work(trip_slot: np.ndarray, L: int, warps: int = 8) -> np.ndarray
     return out
 
 
+TILE_ROWS = 256          # query rows of one attention work item: two 128-row UMMA tiles sharing every K/V chunk
+
+
 def build_attn_tiles(trip_slot: np.ndarray, L: int) -> np.ndarray:
     """Tile list for the tcgen05 attention kernel (``cir_attn_args.tiles``): int32 [W,4] =
-    (first triplet, triplets in the tile, first query row, rows per triplet RB).  A tile is 128 query
-    rows: 128/RB consecutive triplets of ONE candidate run, with RB = L rounded up to a power of two, or
-    a 128-row slice of a single triplet when L > 128."""
+    (first triplet, triplets in the tile, first query row, rows per triplet RB).  A tile is 256 query
+    rows: 256/RB consecutive triplets of ONE candidate run, with RB = L rounded up to a power of two, or
+    a 256-row slice of a single triplet when L > 256."""
     trip_slot = np.asarray(trip_slot)
     if trip_slot.size == 0:
         return np.zeros((0, 4), np.int32)
     assert np.all(np.diff(trip_slot) >= 0), "trip_slot must be candidate-major (sorted)"
-    if L > 128:
-        nslices = (L + 127) // 128
+    if L > TILE_ROWS:
+        nslices = (L + TILE_ROWS - 1) // TILE_ROWS
         t = np.repeat(np.arange(trip_slot.size), nslices)
         out = np.zeros((t.size, 4), np.int32)
         out[:, 0] = t
         out[:, 1] = 1
-        out[:, 2] = np.tile(np.arange(nslices) * 128, trip_slot.size)
-        out[:, 3] = 128
+        out[:, 2] = np.tile(np.arange(nslices) * TILE_ROWS, trip_slot.size)
+        out[:, 3] = TILE_ROWS
         return out
     RB = 1
     while RB < L:
-        RB *= 2                      # rows per triplet padded to a power of two (divides 128)
-    G = 128 // RB
+        RB *= 2                      # rows per triplet padded to a power of two (divides 256)
+    G = TILE_ROWS // RB
     starts = np.flatnonzero(np.r_[True, trip_slot[1:] != trip_slot[:-1]])
     counts = np.diff(np.r_[starts, trip_slot.size])
     ntiles = (counts + G - 1) // G

@@ -128,8 +128,9 @@ typedef struct cir_attn_args {
    * mt = ceil(Lq/16).  NULL: every batch is its own run. */
   const int32_t* work; int32_t num_work;
   /* tcgen05 path (bf16, no key_mask): optional tile list int32 [num_tiles][4] = {first batch, batches in
-   * the tile, first query row, rows per batch RB (a power of two <= 128)}: a tile is 128 query rows =
-   * (128/RB) batches sharing one K/V batch x RB rows starting at `first query row`.  NULL: one batch per tile.
+   * the tile, first query row, rows per batch RB = min(256, smallest power of two >= Lq)}: a tile is 256 query
+   * rows = (256/RB) batches sharing one K/V batch x RB rows starting at `first query row` (two 128-row UMMA tiles
+   * that share every K/V chunk).  NULL: one batch per tile, 256-row slices.
    * kv_batches = number of K/V batches behind k/v (rows = kv_batches*Lk, k_bs must equal Lk*k_rs). */
   const int32_t* tiles; int32_t num_tiles; int32_t kv_batches;
   int32_t B, H, Lq, Lk;

@@ -127,7 +127,7 @@ def test_build_attn_tiles_cover():
         tiles = sched.build_attn_tiles(slot, L)
         rows = set()
         for b0, nb, row0, RB in tiles.tolist():
-            assert nb * RB <= 128 and nb >= 1
+            assert nb * RB <= 256 and nb >= 1
             assert len({slot[b0 + i] for i in range(nb)}) == 1
             for i in range(nb):
                 for r in range(row0, min(row0 + RB, L)):
