@@ -36,6 +36,7 @@ template <int BN, bool PAIR = false> struct Cfg {
   static constexpr int EPI_STAGING = NUM_EPI_WARPS * 4096;   // per-warp 32 x 128 B transpose tiles
   static constexpr int STAGES = (196608 - EPI_STAGING) / STAGE_BYTES;    // 5 (32 KB stages) or 3 (48 KB stages)
   static constexpr int TMEM_COLS = ACC_STAGES * BN;      // 512 / 256
+  static constexpr int VL_BYTES = 3 * ACC_STAGES * BN * 4;   // virtual-LayerNorm variant: column sums, gamma, beta next to the bias rows
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 192 /*barriers*/ + ACC_STAGES * BN * 4 /*bias*/ + EPI_STAGING + 2 * 128 * 2 * 4 /*LayerNorm row statistics*/;
 };
 
@@ -52,6 +53,8 @@ struct Params {
   // m-block back to back, keeps per-row sum / sum of squares, then normalises its rows IN PLACE (re-reading the
   // just-written pre-LN values from L2).  gamma/beta: fp32 [batch][N].
   const float* ln_gamma; const float* ln_beta; float ln_eps; int32_t ln_fuse;
+  // virtual LayerNorm (cir_gemm_ln): see include/cir_b200.h
+  cir_gemm_ln vl;
 };
 
 // tile sequence of one worker: plain round-robin over tiles, or (LayerNorm fusion) round-robin over m-blocks with the
@@ -88,7 +91,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 // ----------------------------------------------------------------------------- the kernel
-template <int BN, bool PAIR, bool LN>
+template <int BN, bool PAIR, bool LN, bool VL>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_c, const Params p) {
@@ -219,6 +222,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     bool tma_store_pending = false;
     float ln_sum = 0.f, ln_sq = 0.f;                       // fused LayerNorm: this thread's row, this warp's column half
     float* sstat = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::EPI_STAGING + 192 + ACC_STAGES * BN * 4);   // [2 halves][128 rows][2]
+    float* svl = sstat + 2 * 128 * 2;                      // VL: [3][ACC_STAGES][BN] column sums | gamma | beta
     int b, m_blk, n_blk;
     for (int it = 0; next_tile(p, worker, num_workers, it, b, m_blk, n_blk); ++it) {
       const int64_t row_base = (int64_t)m_blk * TILE_M + rank * BM + quarter * 32;
@@ -228,6 +232,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (etid < BN) {
         const int64_t n = ntile0 + etid;
         sbias[acc * BN + etid] = (p.bias && n < p.N) ? __ldg(p.bias + b * p.bias_bstride + n) : 0.f;
+        if constexpr (VL) {
+          svl[acc * BN + etid] = (p.vl.a_stats && n < p.N) ? __ldg(p.vl.a_colsum + b * p.vl.colsum_bstride + n) : 0.f;
+          svl[(ACC_STAGES + acc) * BN + etid] = (p.vl.res_stats && n < p.N) ? __ldg(p.vl.res_gamma + b * p.vl.gb_bstride + n) : 0.f;
+          svl[(2 * ACC_STAGES + acc) * BN + etid] = (p.vl.res_stats && n < p.N) ? __ldg(p.vl.res_beta + b * p.vl.gb_bstride + n) : 0.f;
+        }
+      }
+      // virtual LayerNorm: this thread's row statistics of A (a_scale, a_shift) and of the residual (r_scale, r_shift)
+      float a_scale = 1.f, a_shift = 0.f, r_scale = 1.f, r_shift = 0.f, vs_sum = 0.f, vs_sq = 0.f;
+      if constexpr (VL) {
+        auto row_stats = [&](const float* st, int parts, int width, float& scale, float& shift) {
+          const float2* sp = reinterpret_cast<const float2*>(st) + ((int64_t)b * p.M + row) * parts;
+          float s1 = 0.f, s2 = 0.f;
+          for (int i = 0; i < parts; i++) { const float2 t = __ldg(sp + i); s1 += t.x; s2 += t.y; }
+          const float mu = s1 / (float)width;
+          const float var = fmaxf(s2 / (float)width - mu * mu, 0.f);
+          scale = rsqrtf(var + p.vl.eps);
+          shift = -mu * scale;
+        };
+        if (p.vl.a_stats && row_ok) row_stats(p.vl.a_stats, p.vl.a_parts, p.vl.a_width, a_scale, a_shift);
+        if (p.vl.res_stats && row_ok) row_stats(p.vl.res_stats, p.vl.res_parts, p.vl.res_width, r_scale, r_shift);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");       // epilogue warps only
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -257,7 +281,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tmem_ld_wait();
         if (n00 >= p.N) continue;                          // whole span beyond N (warp-uniform)
         float f[64];
-        {
+        if (VL && p.vl.a_stats) {                           // LN(A) W^T = rstd (A W'^T) - rstd mu colsum + bias'
+          const float* sb = sbias + acc * BN + col0;
+          const float* sc = svl + acc * BN + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            f[j] = fmaf(__uint_as_float(v0[j]), a_scale, fmaf(a_shift, sc[j], sb[j]));
+            f[32 + j] = fmaf(__uint_as_float(v1[j]), a_scale, fmaf(a_shift, sc[32 + j], sb[32 + j]));
+          }
+        } else {
           const float4* sb = reinterpret_cast<const float4*>(sbias + acc * BN + col0);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -292,7 +324,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
               for (int q = 0; q < 4; q++) {
                 const float2 t = __bfloat1622float2(h2[q]);
-                f[j * 8 + 2 * q] += t.x; f[j * 8 + 2 * q + 1] += t.y;
+                if (VL && p.vl.res_stats) {                  // residual = LN(raw): (t - mu) rstd gamma + beta
+                  const float* sg = svl + (ACC_STAGES + acc) * BN + col0 + j * 8 + 2 * q;
+                  const float* sbt = svl + (2 * ACC_STAGES + acc) * BN + col0 + j * 8 + 2 * q;
+                  f[j * 8 + 2 * q] += fmaf(t.x, r_scale * sg[0], fmaf(r_shift, sg[0], sbt[0]));
+                  f[j * 8 + 2 * q + 1] += fmaf(t.y, r_scale * sg[1], fmaf(r_shift, sg[1], sbt[1]));
+                } else {
+                  f[j * 8 + 2 * q] += t.x; f[j * 8 + 2 * q + 1] += t.y;
+                }
               }
             }
             __syncwarp();
@@ -317,6 +356,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
             for (int q = 0; q < 4; q++) h2[q] = __floats2bfloat162_rn(f[j * 8 + 2 * q], f[j * 8 + 2 * q + 1]);
+            if (VL && p.vl.out_stats) {                      // partial row statistics of the ROUNDED values a consumer will read
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const float2 t = __bfloat1622float2(h2[q]);
+                vs_sum += t.x + t.y;
+                vs_sq = fmaf(t.x, t.x, fmaf(t.y, t.y, vs_sq));
+              }
+            }
             if constexpr (LN) {                             // statistics of the ROUNDED values the in-place pass will read back
 #pragma unroll
               for (int q = 0; q < 4; q++) {
@@ -380,6 +427,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
           }
         }
+      }
+      if (VL && p.vl.out_stats && row_ok) {                  // this warp's 128 columns of this row
+        float2* op = reinterpret_cast<float2*>(p.vl.out_stats) + ((int64_t)b * p.M + row) * (p.n_blocks * 2) + n_blk * 2 + half;
+        *op = make_float2(vs_sum, vs_sq);
       }
       // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator back
       tcgen05_fence_before();
@@ -521,12 +572,12 @@ static int make_map_c(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t 
   return cir_make_map_3d(ctx, map, base, N, M, batch, ldc, c_bstride, 64, 32, 1);
 }
 
-template <int BN, bool PAIR, bool LN>
+template <int BN, bool PAIR, bool LN, bool VL = false>
 static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc) {
   using C = tc::Cfg<BN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    CIR_CUDA(cudaFuncSetAttribute(tc::gemm_tcgen05_kernel<BN, PAIR, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CIR_CUDA(cudaFuncSetAttribute(tc::gemm_tcgen05_kernel<BN, PAIR, LN, VL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES + (VL ? C::VL_BYTES : 0)));
     attr_set = true;
   }
   const int slots = PAIR ? ctx->num_sms / 2 : ctx->num_sms;
@@ -534,7 +585,7 @@ static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, c
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(PAIR ? 2 * workers : workers);
   cfg.blockDim = dim3(tc::THREADS);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.dynamicSmemBytes = C::SMEM_BYTES + (VL ? C::VL_BYTES : 0);
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -544,7 +595,7 @@ static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, c
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cir_prof_gemm_begin(ctx, 2.0 * (double)p.M * (double)p.N * (double)p.K * (double)p.batch);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_tcgen05_kernel<BN, PAIR, LN>, ma, mw, mc, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_tcgen05_kernel<BN, PAIR, LN, VL>, ma, mw, mc, p);
   cir_prof_gemm_end(ctx);
   if (e != cudaSuccess) { cir_set_error("tcgen05 GEMM launch failed: %s", cudaGetErrorString(e)); return CIR_ECUDA; }
   CIR_LAUNCH_CHECK(ctx);
@@ -563,7 +614,7 @@ int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a) {
   CIR_CHECK_ARG(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->W & 15) == 0, "tcgen05 GEMM: A and W must be 16 B aligned");
   CIR_CHECK_ARG(a->batch == 1 || (a->a_bstride % a->lda == 0 && a->w_bstride % a->ldw == 0),
                 "tcgen05 GEMM: batch strides must be whole rows");
-  tc::Params p;
+  tc::Params p{};
   p.C = a->C; p.bias = a->bias; p.residual = a->residual;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.ldc = a->ldc; p.ldres = a->ldres;
@@ -579,7 +630,7 @@ int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a) {
   const int64_t tiles256 = ((a->M + tc::BM - 1) / tc::BM) * ((a->N + 255) / 256) * a->batch;
   const int64_t pair_tiles = ((a->M + 2 * tc::BM - 1) / (2 * tc::BM)) * ((a->N + 255) / 256) * a->batch;
   const bool use_pair = ctx->gemm_pair && pair_tiles >= ctx->num_sms / 2;
-  const bool use128 = !use_pair && ((a->N <= 128) || (tiles256 < ctx->num_sms));
+  const bool use128 = !use_pair && !a->ln && ((a->N <= 128) || (tiles256 < ctx->num_sms));
   const int BN = use128 ? 128 : 256;
   const int tile_m = use_pair ? 2 * tc::BM : tc::BM;
   p.m_blocks = (int32_t)((a->M + tile_m - 1) / tile_m);
@@ -604,6 +655,13 @@ int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a) {
       (a->batch == 1 || (a->c_bstride % 8) == 0) && a->M < (1ll << 31)) {
     CIR_TRY(make_map_c(ctx, &mc, a->C, a->N, a->M, a->batch, a->ldc, a->c_bstride));
     p.tma_store = 1;
+  }
+  if (a->ln) {
+    CIR_CHECK_ARG(!p.ln_fuse && !use128 && !a->c_f32 && (a->ldc % 8) == 0 && (a->N % 64) == 0, "virtual LayerNorm needs 256-wide tiles and a bf16 output with N % 64 == 0");
+    CIR_CHECK_ARG(!a->ln->out_stats || (a->N % 256) == 0, "virtual LayerNorm: out_stats needs N % 256 == 0");
+    CIR_CHECK_ARG(!a->ln->res_stats || (a->residual && !a->res_f32 && (a->ldres % 8) == 0), "virtual LayerNorm: res_stats needs a bf16 residual with ldres % 8 == 0");
+    p.vl = *a->ln;
+    return use_pair ? launch_tc<256, true, false, true>(ctx, p, ma, mw, mc) : launch_tc<256, false, false, true>(ctx, p, ma, mw, mc);
   }
   if (use_pair) return p.ln_fuse ? launch_tc<256, true, true>(ctx, p, ma, mw, mc) : launch_tc<256, true, false>(ctx, p, ma, mw, mc);
   if (use128) return launch_tc<128, false, false>(ctx, p, ma, mw, mc);

@@ -133,6 +133,7 @@ extern "C" int cir_gemm(cir_ctx* ctx, const cir_gemm_args* a) {
   CIR_CHECK_ARG(a && a->A && a->W && a->C, "gemm: null operand");
   CIR_CHECK_ARG(a->M >= 0 && a->N >= 0 && a->K > 0 && a->batch >= 0, "gemm: bad shape M=%lld N=%lld K=%lld", (long long)a->M, (long long)a->N, (long long)a->K);
   const bool tc = ctx->dtype == CIR_DTYPE_BF16 && ctx->gemm_impl != CIR_GEMM_SIMT;
+  CIR_CHECK_ARG(!a->ln || tc, "gemm: the virtual-LayerNorm extension needs the tcgen05 path (bf16 context)");
   return tc ? cir_gemm_tcgen05(ctx, a) : cir_gemm_simt(ctx, a);
 }
 

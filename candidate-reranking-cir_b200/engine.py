@@ -393,8 +393,10 @@ class Engine:
         return hits.cpu().tolist()
 
     # ------------------------------------------------------------------ primitive ops (tests)
-    def gemm(self, A, W, bias=None, residual=None, act=N.ACT_NONE, out_f32=False):
-        """A [B?,M,K], W [B?,N,K] in act dtype -> C; thin test hook over cir_gemm."""
+    def gemm(self, A, W, bias=None, residual=None, act=N.ACT_NONE, out_f32=False, ln=None):
+        """A [B?,M,K], W [B?,N,K] in act dtype -> C; thin test hook over cir_gemm.
+        ``ln``: dict for the virtual-LayerNorm extension (cir_gemm_ln): a_stats [B,M,P,2] + a_colsum [B,N];
+        res_stats [B,M,P,2] + res_gamma/res_beta [B,N]; out_stats=True -> returns (C, stats [B,M,N/128,2]); eps."""
         batched = A.dim() == 3
         A3 = A if batched else A[None]
         W3 = W if W.dim() == 3 else W[None]
@@ -418,9 +420,30 @@ class Engine:
         g.batch, g.act = Bn, act
         g.c_f32 = 1 if c_dtype == torch.float32 else 0
         g.res_f32 = 1 if (residual is not None and residual.dtype == torch.float32) else 0
+        keep, stats = [], None
+        if ln is not None:
+            e = N.GemmLn()
+            f32 = lambda t: t.to(self.device, torch.float32).contiguous()
+            if "a_stats" in ln:
+                a_st, a_cs = f32(ln["a_stats"]), f32(ln["a_colsum"]).view(Bn, Nn)
+                e.a_stats, e.a_colsum, e.colsum_bstride = N.ptr(a_st), N.ptr(a_cs), Nn
+                e.a_parts, e.a_width = a_st.shape[-2], K
+                keep += [a_st, a_cs]
+            if "res_stats" in ln:
+                r_st, r_g, r_b = f32(ln["res_stats"]), f32(ln["res_gamma"]).view(Bn, Nn), f32(ln["res_beta"]).view(Bn, Nn)
+                e.res_stats, e.res_gamma, e.res_beta, e.gb_bstride = N.ptr(r_st), N.ptr(r_g), N.ptr(r_b), Nn
+                e.res_parts, e.res_width = r_st.shape[-2], Nn
+                keep += [r_st, r_g, r_b]
+            if ln.get("out_stats"):
+                stats = torch.zeros(Bn, M, Nn // 128, 2, dtype=torch.float32, device=self.device)
+                e.out_stats = N.ptr(stats)
+            e.eps = float(ln.get("eps", 1e-12))
+            g.ln = C.pointer(e)
+            keep.append(e)
         self._sync_stream()
         N.check(self._lib.cir_gemm(self.ctx, C.byref(g)), "cir_gemm")
-        return Cm if batched else Cm[0]
+        out = Cm if batched else Cm[0]
+        return (out, stats) if stats is not None else out
 
     def attention(self, q, k, v, key_mask=None, kv_index=None, scale=0.125, work=None, tiles=None):
         """q [B,Lq,H*64], k/v [Bk,Lk,H*64] act dtype -> o [B,Lq,H*64]; test hook over cir_attention."""

@@ -26,12 +26,18 @@ class CirError(RuntimeError):
     pass
 
 
+class GemmLn(C.Structure):
+    _fields_ = [("a_stats", vp), ("a_colsum", vp), ("res_stats", vp), ("res_gamma", vp), ("res_beta", vp), ("out_stats", vp),
+                ("colsum_bstride", i64), ("gb_bstride", i64),
+                ("a_parts", i32), ("a_width", i32), ("res_parts", i32), ("res_width", i32), ("eps", C.c_float)]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [("A", vp), ("W", vp), ("C", vp), ("bias", vp), ("residual", vp),
                 ("M", i64), ("N", i64), ("K", i64),
                 ("lda", i64), ("ldw", i64), ("ldc", i64), ("ldres", i64),
                 ("a_bstride", i64), ("w_bstride", i64), ("c_bstride", i64), ("bias_bstride", i64), ("res_bstride", i64),
-                ("batch", i32), ("act", i32), ("c_f32", i32), ("res_f32", i32)]
+                ("batch", i32), ("act", i32), ("c_f32", i32), ("res_f32", i32), ("ln", C.POINTER(GemmLn))]
 
 
 class AttnArgs(C.Structure):

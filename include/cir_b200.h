@@ -92,6 +92,25 @@ int  cir_profile_gemm_read(cir_ctx* ctx, double* total_ms, double* total_flops, 
  * W: [batch][N, K] act dtype, row stride ldw, batch stride w_bstride
  * C: [batch][M, N] bf16/fp32 (c_f32), row stride ldc, batch stride c_bstride
  * bias: fp32 [batch][N] or NULL; residual: [batch][M,N] (fp32 if res_f32 else act dtype) or NULL */
+/* Optional "virtual LayerNorm" extension of cir_gemm (tcgen05 path, bf16, N % 256 == 0 for out_stats): a LayerNorm
+ * between two GEMMs is never materialised.  The producer writes the pre-LN tensor plus partial row statistics
+ * (out_stats); the consumer multiplies the RAW tensor with gamma-folded weights and applies the normalisation in its
+ * epilogue (a_stats); a GEMM that adds LN(x) as its residual normalises the raw tile on the fly (res_stats).
+ * Replaces nn.LayerNorm of src/nlvr_encoder.py:256,260-264,397 without the extra HBM round trip.
+ *   statistics: fp32 [batch][M][parts][2] = (sum, sum of squares) over `width / parts` columns each.
+ *   a_stats    : C = rstd_r * (A W'^T) - rstd_r mu_r a_colsum[n] + bias[n], with W' = W diag(gamma) (the W passed),
+ *                a_colsum[n] = sum_k W'[n,k], bias[n] = b[n] + sum_k W[n,k] beta[k]  (all prepared by the caller)
+ *   res_stats  : residual term = (res - mu_r) rstd_r res_gamma[n] + res_beta[n]
+ *   out_stats  : partial statistics of the bf16-rounded output, parts = N / 128 */
+typedef struct cir_gemm_ln {
+  const float* a_stats; const float* a_colsum;
+  const float* res_stats; const float* res_gamma; const float* res_beta;
+  float* out_stats;
+  int64_t colsum_bstride, gb_bstride;      /* batch strides of a_colsum and of res_gamma / res_beta (0 = shared) */
+  int32_t a_parts, a_width, res_parts, res_width;
+  float eps;
+} cir_gemm_ln;
+
 typedef struct cir_gemm_args {
   const void* A; const void* W; void* C;
   const float* bias; const void* residual;
@@ -102,6 +121,7 @@ typedef struct cir_gemm_args {
   int32_t act;       /* CIR_ACT_* */
   int32_t c_f32;     /* 1: C is fp32 regardless of ctx dtype */
   int32_t res_f32;   /* 1: residual is fp32 */
+  const cir_gemm_ln* ln;   /* NULL: plain GEMM */
 } cir_gemm_args;
 int cir_gemm(cir_ctx* ctx, const cir_gemm_args* args);
 
