@@ -20,6 +20,7 @@ struct cir_ctx {
   int gemm_pair;        // 1 = allow cta_group::2 pair tiles for large GEMMs (default)
   int prune_last;       // 1 = stage II computes the last layer for the CLS rows only (default)
   int gemm_tma_store;   // 1 = bf16 GEMM outputs leave through TMA bulk tensor stores (default)
+  int virtual_ln;       // 1 = stage-II self / FFN LayerNorms are never materialised (cir_gemm_ln), when the weights carry folded copies
   int fuse_ln;          // 1 = LayerNorm fused into the N=768 pair-tile GEMM epilogues where eligible (default)
   const float* ln_gamma; const float* ln_beta; float ln_eps;   // set around ONE cir_gemm call to request the fused LayerNorm
   cudaStream_t stream;
@@ -96,6 +97,8 @@ __device__ __forceinline__ float warp_max(float v) {
 int cir_gemm_simt(cir_ctx* ctx, const cir_gemm_args* a);
 int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a);
 // 2-D bf16 tensor map over a [rows, K] row-major matrix (row stride ld elements), box [box_rows, 64], SWIZZLE_128B
+int cir_ln_cross_virtual(cir_ctx* ctx, const void* raw, const float* stats, int parts, const float* g1, const float* b1, const void* m,
+                         int64_t m_rows, const float* g2, const float* b2, int64_t rows_per_group, void* y, int64_t rows, float eps);
 int cir_make_map_2d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows);
 // 3-D bf16 map, SWIZZLE_128B: dims (d0 contiguous, d1 stride s1, d2 stride s2; strides in elements), box (b0 <= 64, b1, b2)
 int cir_make_map_3d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1, int64_t s2,

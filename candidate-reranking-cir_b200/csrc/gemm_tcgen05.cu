@@ -282,12 +282,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (n00 >= p.N) continue;                          // whole span beyond N (warp-uniform)
         float f[64];
         if (VL && p.vl.a_stats) {                           // LN(A) W^T = rstd (A W'^T) - rstd mu colsum + bias'
-          const float* sb = sbias + acc * BN + col0;
-          const float* sc = svl + acc * BN + col0;
+          const float4* sb = reinterpret_cast<const float4*>(sbias + acc * BN + col0);
+          const float4* sc = reinterpret_cast<const float4*>(svl + acc * BN + col0);
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            f[j] = fmaf(__uint_as_float(v0[j]), a_scale, fmaf(a_shift, sc[j], sb[j]));
-            f[32 + j] = fmaf(__uint_as_float(v1[j]), a_scale, fmaf(a_shift, sc[32 + j], sb[32 + j]));
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b0 = sb[j >> 2], b1 = sb[8 + (j >> 2)], c0 = sc[j >> 2], c1 = sc[8 + (j >> 2)];
+            f[j] = fmaf(__uint_as_float(v0[j]), a_scale, fmaf(a_shift, c0.x, b0.x));
+            f[j + 1] = fmaf(__uint_as_float(v0[j + 1]), a_scale, fmaf(a_shift, c0.y, b0.y));
+            f[j + 2] = fmaf(__uint_as_float(v0[j + 2]), a_scale, fmaf(a_shift, c0.z, b0.z));
+            f[j + 3] = fmaf(__uint_as_float(v0[j + 3]), a_scale, fmaf(a_shift, c0.w, b0.w));
+            f[32 + j] = fmaf(__uint_as_float(v1[j]), a_scale, fmaf(a_shift, c1.x, b1.x));
+            f[32 + j + 1] = fmaf(__uint_as_float(v1[j + 1]), a_scale, fmaf(a_shift, c1.y, b1.y));
+            f[32 + j + 2] = fmaf(__uint_as_float(v1[j + 2]), a_scale, fmaf(a_shift, c1.z, b1.z));
+            f[32 + j + 3] = fmaf(__uint_as_float(v1[j + 3]), a_scale, fmaf(a_shift, c1.w, b1.w));
           }
         } else {
           const float4* sb = reinterpret_cast<const float4*>(sbias + acc * BN + col0);
@@ -322,14 +329,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               const uint4 rv = lds128(stg + (uint32_t)lane * 128 + (uint32_t)((j ^ (lane & 7)) << 4));
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-              for (int q = 0; q < 4; q++) {
-                const float2 t = __bfloat1622float2(h2[q]);
-                if (VL && p.vl.res_stats) {                  // residual = LN(raw): (t - mu) rstd gamma + beta
-                  const float* sg = svl + (ACC_STAGES + acc) * BN + col0 + j * 8 + 2 * q;
-                  const float* sbt = svl + (2 * ACC_STAGES + acc) * BN + col0 + j * 8 + 2 * q;
-                  f[j * 8 + 2 * q] += fmaf(t.x, r_scale * sg[0], fmaf(r_shift, sg[0], sbt[0]));
-                  f[j * 8 + 2 * q + 1] += fmaf(t.y, r_scale * sg[1], fmaf(r_shift, sg[1], sbt[1]));
-                } else {
+              if (VL && p.vl.res_stats) {                    // residual = LN(raw): (t - mu) rstd gamma + beta
+                const float4* sg = reinterpret_cast<const float4*>(svl + (ACC_STAGES + acc) * BN + col0 + j * 8);
+                const float4* sbt = reinterpret_cast<const float4*>(svl + (2 * ACC_STAGES + acc) * BN + col0 + j * 8);
+                const float4 g0 = sg[0], g1 = sg[1], e0 = sbt[0], e1 = sbt[1];
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                  const float2 t = __bfloat1622float2(h2[q]);
+                  f[j * 8 + 2 * q] += fmaf(fmaf(t.x, r_scale, r_shift), gg[2 * q], ee[2 * q]);
+                  f[j * 8 + 2 * q + 1] += fmaf(fmaf(t.y, r_scale, r_shift), gg[2 * q + 1], ee[2 * q + 1]);
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                  const float2 t = __bfloat1622float2(h2[q]);
                   f[j * 8 + 2 * q] += t.x; f[j * 8 + 2 * q + 1] += t.y;
                 }
               }

@@ -121,6 +121,7 @@ extern "C" int cir_set_attention_impl(cir_ctx* ctx, int impl) {
 }
 extern "C" int cir_set_prune_last_layer(cir_ctx* ctx, int enable) { ctx->prune_last = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_set_fuse_layernorm(cir_ctx* ctx, int enable) { ctx->fuse_ln = enable ? 1 : 0; return CIR_OK; }
+extern "C" int cir_set_virtual_layernorm(cir_ctx* ctx, int enable) { ctx->virtual_ln = enable; return CIR_OK; }   // 1 both, 2 self-LN only, 3 FFN-LN only
 extern "C" int cir_set_gemm_tma_store(cir_ctx* ctx, int enable) { ctx->gemm_tma_store = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_get_dtype(const cir_ctx* ctx) { return ctx->dtype; }
 extern "C" int64_t cir_launch_count(cir_ctx* ctx, int reset) {
@@ -155,8 +156,9 @@ struct Bump {
 // thin wrapper: C[batch][M,N] = act(A W^T + bias) (+res)
 int gemm(cir_ctx* ctx, const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw, int64_t w_bs, const float* bias,
          int64_t bias_bs, void* C, int64_t ldc, int64_t c_bs, int c_f32, const void* res, int64_t ldres, int64_t res_bs, int res_f32,
-         int64_t M, int64_t N, int64_t K, int batch, int act) {
+         int64_t M, int64_t N, int64_t K, int batch, int act, const cir_gemm_ln* ln = nullptr) {
   cir_gemm_args g{};
+  g.ln = ln;
   g.A = A; g.W = W; g.C = C; g.bias = bias; g.residual = res;
   g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldc = ldc; g.ldres = ldres;
   g.a_bstride = a_bs; g.w_bstride = w_bs; g.c_bstride = c_bs; g.bias_bstride = bias_bs; g.res_bstride = res_bs;
@@ -332,7 +334,8 @@ extern "C" int cir_stage1_gallery_embed(cir_ctx* ctx, const cir_stage1_weights* 
 }
 
 // ========================================================================================== stage II
-struct S2Ws { void *cand, *kv, *emb, *h, *qkv, *ctx, *pre, *a, *qc, *ctxc, *m, *x, *f, *feats; float* hid; size_t total; };
+struct S2Ws { void *cand, *kv, *emb, *h, *qkv, *ctx, *pre, *a, *qc, *ctxc, *m, *x, *f, *feats; float *hid, *st1, *st3; size_t total; };
+constexpr int VLN_PARTS = (int)(CIR_HIDDEN / 128);    // partial row statistics per 768-wide row (cir_gemm_ln.out_stats)
 static S2Ws s2_plan(const cir_ctx* ctx, void* ws, size_t bytes, int64_t T, int64_t C, int64_t Q, int64_t L, int64_t N) {
   const size_t es = act_size(ctx);
   const int64_t M = T * L;
@@ -353,6 +356,8 @@ static S2Ws s2_plan(const cir_ctx* ctx, void* ws, size_t bytes, int64_t T, int64
   w.f = b.take(2 * M * F * es);
   w.feats = b.take(T * 2 * D * es);
   w.hid = (float*)b.take(T * D * 4);
+  w.st1 = (float*)b.take(2 * M * VLN_PARTS * 2 * 4);
+  w.st3 = (float*)b.take(2 * M * VLN_PARTS * 2 * 4);
   w.total = align_up(b.off, 256);
   return w;
 }
@@ -384,10 +389,23 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
   CIR_TRY(cir_gather_rows(ctx, ws.emb, trip_query, at(ws.h, M * D, es), T, L * D));
 
   const int full_layers = ctx->prune_last ? CIR_LAYERS - 1 : CIR_LAYERS;
+  // Virtual LayerNorm (cir_gemm_ln): the self-attention LayerNorm{A,B} and the FFN LayerNorm of the full layers are never
+  // stored.  ws.a / ws.h then hold the RAW GEMM outputs, st1 / st3 their partial row statistics; consumers normalise
+  // in their epilogues (folded weights vcq_* / vq_*), only the cross-attention LayerNorm stays a kernel.
+  const bool vln = ctx->virtual_ln && ctx->dtype == CIR_DTYPE_BF16 && ctx->gemm_impl != CIR_GEMM_SIMT && w->vcq_w[0] && w->vq_w[1];
+  const bool vln1 = vln && ctx->virtual_ln != 3, vln3 = vln && ctx->virtual_ln != 2;
+  bool h_raw = false;                                         // ws.h = raw FFN output of the previous layer (+ st3)
   for (int i = 0; i < full_layers; i++) {                                                                          // nlvr_encoder.py:506
     // ---- twin self-attention (:281-289, :346-363): separate weights per stream, shared padding mask (:774)
-    CIR_TRY(gemm(ctx, ws.h, D, M * D, w->self_qkv_w[i], D, 3 * D * D, w->self_qkv_b[i], 3 * D, ws.qkv, 3 * D, M * 3 * D, 0,
-                 nullptr, 0, 0, 0, M, 3 * D, D, 2, CIR_ACT_NONE));
+    if (h_raw) {
+      cir_gemm_ln e{};
+      e.a_stats = ws.st3; e.a_colsum = w->vq_colsum[i]; e.colsum_bstride = 3 * D; e.a_parts = VLN_PARTS; e.a_width = (int32_t)D; e.eps = BERT_EPS;
+      CIR_TRY(gemm(ctx, ws.h, D, M * D, w->vq_w[i], D, 3 * D * D, w->vq_b[i], 3 * D, ws.qkv, 3 * D, M * 3 * D, 0,
+                   nullptr, 0, 0, 0, M, 3 * D, D, 2, CIR_ACT_NONE, &e));
+    } else {
+      CIR_TRY(gemm(ctx, ws.h, D, M * D, w->self_qkv_w[i], D, 3 * D * D, w->self_qkv_b[i], 3 * D, ws.qkv, 3 * D, M * 3 * D, 0,
+                   nullptr, 0, 0, 0, M, 3 * D, D, 2, CIR_ACT_NONE));
+    }
     for (int s = 0; s < 2; s++) {
       cir_attn_args a{};
       void* qkv_s = at(ws.qkv, s * M * 3 * D, es);
@@ -398,11 +416,30 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
       CIR_TRY(cir_attention(ctx, &a));
     }
     // a_s = LayerNorm{A,B}(dense_s(ctx_s) + h_s)   (:261-264)
-    CIR_TRY(gemm_layernorm(ctx, ws.ctx, D, M * D, w->self_out_w[i], D, D * D, w->self_out_b[i], D, ws.h, D, M * D,
-                           w->self_ln_g[i], w->self_ln_b[i], BERT_EPS, ws.pre, ws.a, M, D, 2));
+    if (vln1 || h_raw) {                                       // ws.a = raw dense_s(ctx_s) + h_s, st1 = its row statistics
+      cir_gemm_ln e{};
+      e.out_stats = vln1 ? ws.st1 : nullptr; e.eps = BERT_EPS;
+      if (h_raw) {
+        e.res_stats = ws.st3; e.res_gamma = w->ffn_ln_g[i - 1]; e.res_beta = w->ffn_ln_b[i - 1]; e.gb_bstride = 0;
+        e.res_parts = VLN_PARTS; e.res_width = (int32_t)D;
+      }
+      CIR_TRY(gemm(ctx, ws.ctx, D, M * D, w->self_out_w[i], D, D * D, w->self_out_b[i], D, vln1 ? ws.a : ws.pre, D, M * D, 0, ws.h, D, M * D, 0,
+                   M, D, D, 2, CIR_ACT_NONE, &e));
+      if (!vln1) CIR_TRY(cir_add_layernorm(ctx, ws.pre, 0, 2 * M, nullptr, w->self_ln_g[i], w->self_ln_b[i], M, ws.a, 0, 2 * M, BERT_EPS));
+    } else {
+      CIR_TRY(gemm_layernorm(ctx, ws.ctx, D, M * D, w->self_out_w[i], D, D * D, w->self_out_b[i], D, ws.h, D, M * D,
+                             w->self_ln_g[i], w->self_ln_b[i], BERT_EPS, ws.pre, ws.a, M, D, 2));
+    }
     // ---- twin cross-attention onto the SAME candidate tokens (:322-339)
-    CIR_TRY(gemm(ctx, ws.a, D, M * D, w->cross_q_w[i], D, D * D, w->cross_q_b[i], D, ws.qc, D, M * D, 0, nullptr, 0, 0, 0,
-                 M, D, D, 2, CIR_ACT_NONE));
+    if (vln1) {
+      cir_gemm_ln e{};
+      e.a_stats = ws.st1; e.a_colsum = w->vcq_colsum[i]; e.colsum_bstride = D; e.a_parts = VLN_PARTS; e.a_width = (int32_t)D; e.eps = BERT_EPS;
+      CIR_TRY(gemm(ctx, ws.a, D, M * D, w->vcq_w[i], D, D * D, w->vcq_b[i], D, ws.qc, D, M * D, 0, nullptr, 0, 0, 0,
+                   M, D, D, 2, CIR_ACT_NONE, &e));
+    } else {
+      CIR_TRY(gemm(ctx, ws.a, D, M * D, w->cross_q_w[i], D, D * D, w->cross_q_b[i], D, ws.qc, D, M * D, 0, nullptr, 0, 0, 0,
+                   M, D, D, 2, CIR_ACT_NONE));
+    }
     // K/V projections once per candidate image: rows K0|V0|K1|V1 (:158-159)
     CIR_TRY(gemm(ctx, ws.cand, D, 0, w->cross_kv_w[i], D, 0, w->cross_kv_b[i], 0, ws.kv, 4 * D, 0, 0, nullptr, 0, 0, 0,
                  C * N, 4 * D, D, 1, CIR_ACT_NONE));
@@ -420,11 +457,24 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
     // m = merge(dense0(c0), dense1(c1)) folded into one K=1536 GEMM (:250-258); x_s = LayerNorm{A,B}(m + a_s) (:256,:260)
     CIR_TRY(gemm(ctx, ws.ctxc, 2 * D, 0, w->cross_out_w[i], 2 * D, 0, w->cross_out_b[i], 0, ws.m, D, 0, 0, nullptr, 0, 0, 0,
                  M, D, 2 * D, 1, CIR_ACT_NONE));
-    CIR_TRY(cir_add_layernorm(ctx, ws.m, 0, M, ws.a, w->cross_ln_g[i], w->cross_ln_b[i], M, ws.x, 0, 2 * M, BERT_EPS));
+    if (vln1) {                                                // a_s = LN(raw) on the fly from st1
+      CIR_TRY(cir_ln_cross_virtual(ctx, ws.a, ws.st1, VLN_PARTS, w->self_ln_g[i], w->self_ln_b[i], ws.m, M, w->cross_ln_g[i],
+                                   w->cross_ln_b[i], M, ws.x, 2 * M, BERT_EPS));
+    } else {
+      CIR_TRY(cir_add_layernorm(ctx, ws.m, 0, M, ws.a, w->cross_ln_g[i], w->cross_ln_b[i], M, ws.x, 0, 2 * M, BERT_EPS));
+    }
     // ---- FFN, weights shared by both streams (:469-476): both streams as 2M rows
     CIR_TRY(gemm(ctx, ws.x, D, 0, w->ffn1_w[i], D, 0, w->ffn1_b[i], 0, ws.f, F, 0, 0, nullptr, 0, 0, 0, 2 * M, F, D, 1, CIR_ACT_GELU));
-    CIR_TRY(gemm_layernorm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.x, D, 0, w->ffn_ln_g[i], w->ffn_ln_b[i], BERT_EPS,
-                           ws.pre, ws.h, 2 * M, F, 1));
+    if (vln3 && i + 1 < full_layers) {                         // ws.h = raw FFN output + x, st3 = its row statistics
+      cir_gemm_ln e{};
+      e.out_stats = ws.st3; e.eps = BERT_EPS;
+      CIR_TRY(gemm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.h, D, 0, 0, ws.x, D, 0, 0, 2 * M, D, F, 1, CIR_ACT_NONE, &e));
+      h_raw = true;
+    } else {
+      CIR_TRY(gemm_layernorm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.x, D, 0, w->ffn_ln_g[i], w->ffn_ln_b[i], BERT_EPS,
+                             ws.pre, ws.h, 2 * M, F, 1));
+      h_raw = false;
+    }
   }
   if (ctx->prune_last) {
     // ---- last layer, CLS rows only.  The encoder returns cat(h0[:,0,:], h1[:,0,:]) (nlvr_encoder.py:906-909), so

@@ -60,6 +60,10 @@ class Engine:
         """bf16 GEMM outputs through TMA bulk tensor stores (default on) or per-lane 16 B stores."""
         N.check(self._lib.cir_set_gemm_tma_store(self.ctx, 1 if enable else 0))
 
+    def set_virtual_layernorm(self, enable: bool):
+        """stage II: never materialise the self-attention / FFN LayerNorms (cir_gemm_ln); bf16 only."""
+        N.check(self._lib.cir_set_virtual_layernorm(self.ctx, int(enable)))
+
     def set_fuse_layernorm(self, enable: bool):
         """bf16 mode: LayerNorm inside the FFN2 GEMM epilogue (opt-in; default is the separate LayerNorm kernel)."""
         N.check(self._lib.cir_set_fuse_layernorm(self.ctx, 1 if enable else 0))
@@ -229,11 +233,46 @@ class Engine:
             w.ffn2_b[i] = self._cat_p(sd, [p + "output.dense.bias"], keep)
             w.ffn_ln_g[i] = self._cat_p(sd, [p + "output.LayerNorm.weight"], keep)
             w.ffn_ln_b[i] = self._cat_p(sd, [p + "output.LayerNorm.bias"], keep)
+        if self.precision == "bf16":
+            self._pack_virtual_ln(sd, w, keep)
         w.cls0_w = self._cat_w(sd, ["cls_head.0.weight"], keep)
         w.cls0_b = self._cat_p(sd, ["cls_head.0.bias"], keep)
         t = self._p(sd["cls_head.2.weight"][0]); keep.append(t); w.cls2_w = N.ptr(t)       # class-0 row only (:136)
         t = self._p(sd["cls_head.2.bias"][0:1]); keep.append(t); w.cls2_b = N.ptr(t)
         return w, keep
+
+    def _fold_ln(self, Ws, bs, gammas, betas, keep):
+        """LN(x) W^T + b == rstd (x W'^T) - rstd mu colsum + b'  with W' = W diag(gamma) (rounded to bf16, and colsum
+        taken from the ROUNDED values so that the mean term cancels exactly), b' = b + W beta.  float64 composition.
+        Ws/bs/gammas/betas: per-batch lists -> (ptr W' [B][N,K] bf16, ptr b' [B][N], ptr colsum [B][N])."""
+        Wf, bf, cs = [], [], []
+        for W, b, g, be in zip(Ws, bs, gammas, betas):
+            W, b, g, be = W.double(), b.double(), g.double(), be.double()
+            Wr = (W * g[None, :]).to(torch.bfloat16)
+            Wf.append(Wr)
+            cs.append(Wr.double().sum(dim=1))
+            bf.append(b + W @ be)
+        tw = torch.stack(Wf).to(self.device).contiguous()
+        tb = torch.stack(bf).float().to(self.device).contiguous()
+        tc = torch.stack(cs).float().to(self.device).contiguous()
+        keep += [tw, tb, tc]
+        return N.ptr(tw), N.ptr(tb), N.ptr(tc)
+
+    def _pack_virtual_ln(self, sd, w, keep):
+        """Folded weight copies for cir_set_virtual_layernorm (include/cir_b200.h, cir_stage2_weights.vq_* / vcq_*)."""
+        for i in range(LAYERS):
+            p = f"text_encoder.encoder.layer.{i}."
+            a, c = p + "attention.", p + "crossattention."
+            ln = [(sd[a + f"output.LayerNorm{x}.weight"], sd[a + f"output.LayerNorm{x}.bias"]) for x in ("A", "B")]
+            w.vcq_w[i], w.vcq_b[i], w.vcq_colsum[i] = self._fold_ln(
+                [sd[c + f"self{s}.query.weight"] for s in (0, 1)], [sd[c + f"self{s}.query.bias"] for s in (0, 1)],
+                [ln[0][0], ln[1][0]], [ln[0][1], ln[1][1]], keep)
+            if i >= 1:
+                q = f"text_encoder.encoder.layer.{i - 1}."
+                g, be = sd[q + "output.LayerNorm.weight"], sd[q + "output.LayerNorm.bias"]
+                Ws = [torch.cat([sd[a + f"self{s}.{n}.weight"] for n in ("query", "key", "value")], dim=0) for s in (0, 1)]
+                bs = [torch.cat([sd[a + f"self{s}.{n}.bias"] for n in ("query", "key", "value")], dim=0) for s in (0, 1)]
+                w.vq_w[i], w.vq_b[i], w.vq_colsum[i] = self._fold_ln(Ws, bs, [g, g], [be, be], keep)
 
     # ------------------------------------------------------------------ pipelines
     def vit_forward(self, w, images: torch.Tensor, batch: int = 32) -> torch.Tensor:

@@ -76,7 +76,8 @@ class Stage2Weights(C.Structure):
                 ("cross_kv_w", _A), ("cross_kv_b", _A), ("cross_out_w", _A), ("cross_out_b", _A),
                 ("cross_ln_g", _A), ("cross_ln_b", _A), ("ffn1_w", _A), ("ffn1_b", _A),
                 ("ffn2_w", _A), ("ffn2_b", _A), ("ffn_ln_g", _A), ("ffn_ln_b", _A),
-                ("cls0_w", vp), ("cls0_b", vp), ("cls2_w", vp), ("cls2_b", vp)]
+                ("cls0_w", vp), ("cls0_b", vp), ("cls2_w", vp), ("cls2_b", vp),
+                ("vq_w", _A), ("vq_b", _A), ("vq_colsum", _A), ("vcq_w", _A), ("vcq_b", _A), ("vcq_colsum", _A)]
 
 
 _SIGS = {
@@ -89,6 +90,7 @@ _SIGS = {
     "cir_set_attention_impl": (C.c_int, [vp, C.c_int]),
     "cir_set_prune_last_layer": (C.c_int, [vp, C.c_int]),
     "cir_set_fuse_layernorm": (C.c_int, [vp, C.c_int]),
+    "cir_set_virtual_layernorm": (C.c_int, [vp, C.c_int]),
     "cir_set_gemm_tma_store": (C.c_int, [vp, C.c_int]),
     "cir_get_dtype": (C.c_int, [vp]),
     "cir_launch_count": (i64, [vp, C.c_int]),

@@ -71,6 +71,9 @@ int  cir_set_prune_last_layer(cir_ctx* ctx, int enable);
 /* bf16 mode: fuse LayerNorm into the long-K N=768 pair-tile GEMM epilogue (FFN2): statistics in the epilogue, in-place
  * normalisation pass from L2.  Default OFF: measured 53.7k vs 54.4k triplets/s for the separate LayerNorm kernels. */
 int  cir_set_fuse_layernorm(cir_ctx* ctx, int enable);
+/* 1: cir_stage2_score never materialises the self-attention and FFN LayerNorms of the full layers (bf16 only, needs the
+ * folded weight copies of cir_stage2_weights); 0: every LayerNorm is a kernel of its own. */
+int  cir_set_virtual_layernorm(cir_ctx* ctx, int enable);
 /* 1 (default): bf16 GEMM outputs leave the tcgen05 epilogue through TMA bulk tensor stores; 0: per-lane 16 B stores. */
 int  cir_set_gemm_tma_store(cir_ctx* ctx, int enable);
 int  cir_get_dtype(const cir_ctx* ctx);
@@ -282,6 +285,12 @@ typedef struct cir_stage2_weights {
   const float* ffn_ln_g[CIR_LAYERS];    const float* ffn_ln_b[CIR_LAYERS];
   const void*  cls0_w; const float* cls0_b;      /* [768,1536], [768] */
   const float* cls2_w; const float* cls2_b;      /* row 0 of cls_head.2: [768] fp32, [1] */
+  /* Optional gamma-folded copies for the virtual-LayerNorm path (all NULL = path disabled; see cir_gemm_ln):
+   *   vq_*[i]  : self QKV of layer i >= 1 folded with ffn_ln of layer i-1:  W' = W diag(gamma), colsum[n] = sum_k W'[n,k]
+   *              (of the bf16-rounded W'), bias' = b + W beta.  [2][2304,768] bf16, [2][2304] fp32, [2][2304] fp32
+   *   vcq_*[i] : cross query of layer i folded with self_ln{A,B} of layer i.  [2][768,768], [2][768], [2][768] */
+  const void* vq_w[CIR_LAYERS];  const float* vq_b[CIR_LAYERS];  const float* vq_colsum[CIR_LAYERS];
+  const void* vcq_w[CIR_LAYERS]; const float* vcq_b[CIR_LAYERS]; const float* vcq_colsum[CIR_LAYERS];
 } cir_stage2_weights;
 
 /* BLIP_NLVR.img_txt_fusion_val (src/blip_stage2.py:101-136 -> src/nlvr_encoder.py:777-909) for a

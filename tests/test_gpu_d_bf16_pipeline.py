@@ -209,3 +209,35 @@ def test_bf16_vs_fp32_check_mode_at_scale():
     b = m32.score_triplets(z16.float(), ids, mask, tokens32, cand)
     err = (a - b).abs()
     assert err.max() <= 2e-2 and err.mean() < 5e-3, (err.max().item(), err.mean().item())
+
+
+@pytest.mark.parametrize("shape", ["small", "pair_tiles"])
+def test_virtual_layernorm_path(shape):
+    """cir_set_virtual_layernorm: the self-attention / FFN LayerNorms are applied inside the consuming GEMM epilogues
+    (gamma-folded weights + row statistics) instead of being stored.  Same tolerance against the CPU oracle as the
+    default path, and close to the default path itself."""
+    syn_ = cir.synthetic
+    sd1, sd2 = golden_weights(load_golden("pipeline_small.npz"))
+    m2 = cir.blip_stage2.blip_stage2(image_size=384, state_dict=sd2, precision="bf16")
+    eng = m2.engine
+    g = torch.Generator().manual_seed(11)
+    G, Q, K, L = (3, 5, 4, 24) if shape == "small" else (6, 80, 8, 32)       # pair tiles need >= 74 x 256 rows per GEMM
+    tokens = torch.randn(G, 577, 768, generator=g).cuda().bfloat16()
+    ids, mask = syn_.make_token_ids(Q, L, seed=5, min_len=max(8, L - 10))
+    ids[:, 0] = syn_.ENC_TOKEN_ID
+    z_t = torch.randn(Q, L, 768, generator=g).cuda().bfloat16()
+    cand = torch.stack([torch.randint(0, G, (K,), generator=g) for _ in range(Q)]).int()
+    base = m2.score_triplets(z_t, ids, mask, tokens, cand.numpy())
+    eng.set_virtual_layernorm(True)
+    try:
+        virt = m2.score_triplets(z_t, ids, mask, tokens, cand.numpy())
+    finally:
+        eng.set_virtual_layernorm(False)
+    assert torch.isfinite(virt).all()
+    assert (virt - base).abs().max() < 2e-2, (virt - base).abs().max()
+    nq = min(Q, 6)
+    tok_ref, z_ref = tokens.float().cpu(), z_t.float().cpu()
+    with torch.no_grad():
+        want = torch.stack([O.stage2_score(sd2, z_ref[q:q + 1], ids[q:q + 1], mask[q:q + 1], tok_ref[cand[q].long()]) for q in range(nq)])
+    err = (virt[:nq].cpu() - want).abs()
+    assert err.max() <= 2e-2, (err.max(), err.mean())

@@ -1,5 +1,6 @@
 """Quick on-box performance probe (not a bench): GEMM TF/s at the path's shapes, attention time,
 stage-II chunk throughput.  Prints one line per measurement."""
+import os
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -58,6 +59,13 @@ def stage2_probe(T_per=2048, C=48, L=32, reps=3, configs=((1024, 32), (2048, 48)
         ms = timeit(lambda: m2.score_triplets(z_t, ids, mask, tokens, cand), warm=1, it=reps)
         nl = e.launch_count() / (reps + 1)
         print(f"stage2 Q={Q} K={K} L={L} G={G} chunk(T<={mt},C<={mc}): {ms:.1f} ms -> {Q*K/ms*1e3:.0f} triplets/s, {nl:.0f} launches/pass", flush=True)
+        for mode in [int(x) for x in os.environ.get("CIR_PROBE_VLN", "").split(",") if x]:
+            e.set_virtual_layernorm(mode)
+            e.launch_count(reset=True)
+            ms = timeit(lambda: m2.score_triplets(z_t, ids, mask, tokens, cand), warm=1, it=reps)
+            nl = e.launch_count() / (reps + 1)
+            e.set_virtual_layernorm(0)
+            print(f"   virtual LayerNorm mode {mode}: {ms:.1f} ms -> {Q*K/ms*1e3:.0f} triplets/s, {nl:.0f} launches/pass", flush=True)
 
 
 def stage1_probe():
