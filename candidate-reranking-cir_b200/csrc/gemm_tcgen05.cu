@@ -207,6 +207,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t stg = smem_base + C::STAGES * C::STAGE_BYTES + (uint32_t)ew * 4096;                    // this warp's 32 x 128 B tile (4 KB aligned)
     const int etid = threadIdx.x - 64;       // 0..255
     const bool res_bf16_fast = p.residual && !p.res_f32 && (p.ldres & 7) == 0;
+    const bool res_f32_fast = p.residual && p.res_f32 && (p.ldres & 3) == 0 && ((uintptr_t)p.residual & 15) == 0;
     const bool out_bf16_fast = !p.c_f32 && (p.ldc & 7) == 0;
     const bool out_f32_fast = p.c_f32 && (p.ldc & 3) == 0;
     const int lr = lane >> 3, lp = lane & 7; // coalesced mapping: 4 rows x 8 sixteen-byte pieces per instruction
@@ -273,6 +274,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             rq[it] = rg < p.M ? *reinterpret_cast<const uint4*>(rp + rg * p.ldres) : make_uint4(0, 0, 0, 0);
           }
         }
+        // fp32 residual (the ViT's fp32 token stream): the same coalesced fetch, 32 columns (128 B per row) at a time
+        const bool res32_fast = res_f32_fast && span_full;
+        auto load_res32 = [&](int hh) {
+          const float* rp = (const float*)p.residual + b * p.res_bstride + n00 + hh * 32 + lp * 4;
+#pragma unroll
+          for (int it = 0; it < 8; it++) {
+            const int64_t rg = row_base + it * 4 + lr;
+            rq[it] = rg < p.M ? *reinterpret_cast<const uint4*>(rp + rg * p.ldres) : make_uint4(0, 0, 0, 0);
+          }
+        };
+        if (res32_fast) load_res32(0);
         uint32_t v0[32], v1[32];
         __syncwarp();                                      // tcgen05.ld is .sync.aligned: reconverge first
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col0);
@@ -350,6 +362,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               }
             }
             __syncwarp();
+          } else if (res32_fast) {
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+#pragma unroll
+              for (int it = 0; it < 8; it++) sts128(stg + (uint32_t)(it * 4 + lr) * 128 + (uint32_t)((lp ^ ((it * 4 + lr) & 7)) << 4), rq[it]);
+              __syncwarp();
+              if (hh == 0) load_res32(1);                    // in flight while the first half is added
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const uint4 rv = lds128(stg + (uint32_t)lane * 128 + (uint32_t)((j ^ (lane & 7)) << 4));
+                f[hh * 32 + j * 4] += __uint_as_float(rv.x); f[hh * 32 + j * 4 + 1] += __uint_as_float(rv.y);
+                f[hh * 32 + j * 4 + 2] += __uint_as_float(rv.z); f[hh * 32 + j * 4 + 3] += __uint_as_float(rv.w);
+              }
+              __syncwarp();
+            }
           } else if (row_ok) {
             const int64_t ro = b * p.res_bstride + row * p.ldres + n00;
 #pragma unroll
