@@ -421,10 +421,10 @@ int launch_mma(cir_ctx* ctx, const cir_attn_args* a, int mt) {
   const int cpb = (mt + NWARPS - 1) / NWARPS;
   const unsigned gx = a->work ? (unsigned)a->num_work : (unsigned)(a->B * cpb);
   const size_t smem = FA_STAGES * FA_STAGE_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
+  const unsigned bit = 1u << (NWARPS == 2 ? 0 : (NWARPS == 4 ? 1 : 2));     // per context: the attribute is per device
+  if (!(ctx->func_attr_mask & bit)) {
     CIR_CUDA(cudaFuncSetAttribute(attention_mma_kernel<NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    ctx->func_attr_mask |= bit;
   }
   attention_mma_kernel<NWARPS><<<dim3(gx, (unsigned)a->H), NWARPS * 32, smem, ctx->stream>>>(*a, mt);
   CIR_LAUNCH_CHECK(ctx);

@@ -433,10 +433,9 @@ int cir_attention_tc(cir_ctx* ctx, const cir_attn_args* a) {
   CIR_TRY(cir_make_map_3d(ctx, &mo, a->o, (int64_t)a->H * 64, a->Lq, a->B, a->o_rs, a->o_bs, 64, 32, 1));
   CIR_TRY(cir_make_map_2d(ctx, &mk, a->k, kv_rows, (int64_t)a->H * 64, a->k_rs, fatc::KC));
   CIR_TRY(cir_make_map_2d(ctx, &mv, a->v, kv_rows, (int64_t)a->H * 64, a->v_rs, fatc::KC));
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->func_attr_mask & (1u << 3))) {                  // per context: the attribute is per device
     CIR_CUDA(cudaFuncSetAttribute(fatc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fatc::SMEM_BYTES));
-    attr_set = true;
+    ctx->func_attr_mask |= 1u << 3;
   }
   const int cpb = (a->Lq + 255) / 256;
   const int64_t ntiles = a->tiles ? (int64_t)a->num_tiles : (int64_t)a->B * cpb;

@@ -617,10 +617,10 @@ static int make_map_c(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t 
 template <int BN, bool PAIR, bool LN, bool VL = false>
 static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc) {
   using C = tc::Cfg<BN, PAIR>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  const unsigned bit = 1u << (8 + (BN == 128 ? 0 : 1) + (PAIR ? 2 : 0) + (LN ? 4 : 0) + (VL ? 8 : 0));   // per context: the attribute is per device
+  if (!(ctx->func_attr_mask & bit)) {
     CIR_CUDA(cudaFuncSetAttribute(tc::gemm_tcgen05_kernel<BN, PAIR, LN, VL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES + (VL ? C::VL_BYTES : 0)));
-    attr_set = true;
+    ctx->func_attr_mask |= bit;
   }
   const int slots = PAIR ? ctx->num_sms / 2 : ctx->num_sms;
   const int workers = p.num_tiles < slots ? p.num_tiles : slots;

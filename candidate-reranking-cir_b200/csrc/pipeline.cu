@@ -69,6 +69,8 @@ extern "C" int cir_create(cir_ctx** out, int device, int dtype) {
   c->gemm_pair = 1;
   c->prune_last = 1;
   c->gemm_tma_store = 1;
+  c->func_attr_mask = 0;
+  c->virtual_ln = 0;
   c->fuse_ln = 0;   // measured on B200: no gain over the separate HBM-bound LayerNorm kernels, so opt-in
   c->ln_gamma = nullptr; c->ln_beta = nullptr; c->ln_eps = 0.f;
   c->stream = 0;
