@@ -10,19 +10,20 @@
 // item's Q/K/V loads and first S products overlap the current item's tail.
 //
 //   warps 0-3   softmax of tile A, warps 4-7 softmax of tile B: thread r owns query row r == TMEM lane r.  Per
-//               64-key chunk ONE tcgen05.ld sweep brings the row's scores into registers, row max -> exp2 -> bf16 P
-//               written to a 128B-swizzled shared-memory atom (the A operand of the PV product).  S and P are
+//               64-key chunk ONE tcgen05.ld sweep brings the row's scores into registers, row max -> exp2 -> packed bf16
+//               P written straight back into TENSOR memory (tcgen05.st) over the first 32 columns of the S buffer it
+//               came from; the PV product takes its A operand from TMEM, so P never touches shared memory.  S is
 //               double-buffered per tile, so the tensor core computes S_{j+1}, S_{j+2} while the softmax works on
 //               chunk j.  O accumulates in TMEM across chunks; the reference max moves lazily (only when the row
 //               max grew by more than 2^8), so the O rescale (tcgen05.ld / tcgen05.st) is a rare path.
 //   warp 8/9    one elected thread each: all tcgen05.mma issue of tile A / tile B:
 //                 S_j = Q K_j^T  (A=Q smem, B=K_j smem, both K-major)
-//                 O  += P_j V_j  (A=P smem K-major, B=V_j smem MN-major)
+//                 O  += P_j V_j  (A=P in TMEM, B=V_j smem MN-major)
 //               and the commits that hand the K / V ring stages back to the loader (2 arrivals per stage).
 //   warp 10     one elected thread: TMA loads of Q tiles (3-D map, double-buffered per tile) and of the K / V
 //               chunks into 6-deep rings -- deep enough that the L2 -> shared-memory latency under load
 //               (> 1 us) never reaches the MMA issue loop.
-//   TMEM: per tile S0, S1 (64 columns each) + O (64).  Scores and probabilities never touch HBM.
+//   TMEM: per tile S0/P0, S1/P1 (64 columns each) + O (64).  Scores and probabilities never leave the SM.
 #include <algorithm>
 #include <type_traits>
 #include "common.cuh"
@@ -32,15 +33,15 @@ namespace fatc {
 
 using namespace tc;
 
-constexpr int KC = 64;                  // keys per chunk (one 128-byte swizzle atom of P per chunk)
+constexpr int KC = 64;                  // keys per chunk
 constexpr int KS = 6;                   // K / V ring depth
 constexpr int THREADS = 352;            // 8 softmax warps + 2 MMA-issue warps + 1 loader warp
 constexpr int Q_BYTES = 128 * 128;      // 128 rows x 64 bf16
 constexpr int KV_BYTES = KC * 128;      // 64 keys x 64 bf16
-constexpr int P_BYTES = 128 * 128;      // [128 rows x 64 keys] bf16
+constexpr int P_BYTES = 128 * 128;      // O staging tile: [128 rows x 64 dims] bf16
 constexpr int OFF_Q = 0;                               // [tile][item parity]
-constexpr int OFF_P = OFF_Q + 4 * Q_BYTES;             // [tile][chunk parity]
-constexpr int OFF_K = OFF_P + 4 * P_BYTES;
+constexpr int OFF_P = OFF_Q + 4 * Q_BYTES;             // [tile]: staging of the O tile for its TMA store (P itself lives in TMEM)
+constexpr int OFF_K = OFF_P + 2 * P_BYTES;
 constexpr int OFF_V = OFF_K + KS * KV_BYTES;
 constexpr int OFF_BAR = OFF_V + KS * KV_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 512;
@@ -235,9 +236,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           const uint32_t idesc = make_idesc_bf16_bmn(128, 64);
           const int ksteps = n_pad_of(j) >> 4;
           for (int k = 0; k < ksteps; k++) {
-            const uint64_t pdesc = make_smem_desc_sw128(sbase + OFF_P + (t * 2 + (g & 1)) * P_BYTES) + (uint64_t)(k * 2);   // +32 B per 16 keys
+            const uint32_t p_tmem = tm + S_COL + (g & 1) * 64 + k * 8;     // P_g overwrote S_g: 16 keys = 8 packed columns per K step
             const uint64_t vdesc = make_smem_desc_sw128(sbase + OFF_V + s * KV_BYTES + k * 2048);                          // 16 key rows x 128 B
-            umma_bf16(tm + O_COL, pdesc, vdesc, idesc, (uint32_t)((j | k) != 0));
+            umma_bf16_ts(tm + O_COL, p_tmem, vdesc, idesc, (uint32_t)((j | k) != 0));
           }
           umma_commit(pvdone(t, g & 1));
           umma_commit(vempty(s));                            // this tile is done with V stage s
@@ -263,7 +264,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     auto turn_pass = [&]() { asm volatile("bar.arrive %0, 64;" ::"r"(t == 0 ? 1 + wq : 5 + wq) : "memory"); };
     int g = 0;
     Item nxt = n_my > 0 ? decode_rows(p, (int)blockIdx.x, ntiles, cpb) : Item{};
-    bool o_pending = false;                                  // a TMA store of this warp may still be reading its P slice
+    bool o_pending = false;                                  // a TMA store of this warp may still be reading its staging slice
     for (int it_i = 0; it_i < n_my; it_i++) {
       const Item it = nxt;
       if (it_i + 1 < n_my) nxt = decode_rows(p, (int)blockIdx.x + (it_i + 1) * (int)gridDim.x, ntiles, cpb);   // off the critical path
@@ -283,6 +284,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         __syncwarp();
         tmem_ld_32x32b_x32(lane_addr + S_COL + pb * 64, v0);
         if (two) tmem_ld_32x32b_x32(lane_addr + S_COL + pb * 64 + 32, v1);
+        else {
+#pragma unroll
+          for (int x = 0; x < 32; x++) v1[x] = 0u;
+        }
         tmem_ld_wait();
         // ---- row max of the chunk
         float cmax = -INFINITY;
@@ -319,22 +324,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           m = m_new;
           rescale_o(o_addr, alpha);
         }
-        if (g >= 2) mbar_wait(pvdone(t, pb), (uint32_t)(((g - 2) >> 1) & 1));  // P buffer pb: PV_{g-2} has read it
-        // ---- P = exp2(S*c - m) as bf16 into the swizzled A-operand tile (one 128 B row per thread); padded keys -> 0.
-        //      Two instantiations: full chunks carry no per-element masking; the tail chunk only touches the
-        //      padded-to-16 keys the PV product reads.
-        if (o_pending) {                                     // the previous item's O tile left through this warp's P slice
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          __syncwarp();
-          o_pending = false;
-        }
-        uint8_t* prow = smem + OFF_P + (t * 2 + pb) * P_BYTES + r * 128;
-        auto exp_store = [&](auto full_tag) {
+        // ---- P = exp2(S*c - m) as packed bf16 back into TENSOR memory, over the first 32 columns of the S buffer it was
+        //      read from (the A operand of the PV product comes from TMEM: no shared-memory round trip, no proxy fence).
+        //      PV_{g-2}, the last reader of these columns, retired before S_g was written (in-order pipe), so no wait.
+        //      Two instantiations: full chunks carry no per-element masking; the tail chunk zero-fills the padded keys.
+        auto exp_pack = [&](auto full_tag) {
           constexpr bool FULL = decltype(full_tag)::value;
-          const int npad = (keys + 15) & ~15;
 #pragma unroll
           for (int c = 0; c < 8; c++) {
-            if (!FULL && c * 8 >= npad) continue;
             float e[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
@@ -344,17 +341,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
               if (!FULL && x >= keys) e[q] = 0.f;
             }
             l += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-            uint4 w;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w);
 #pragma unroll
-            for (int q = 0; q < 4; q++) h2[q] = __floats2bfloat162_rn(e[2 * q], e[2 * q + 1]);
-            *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = w;
+            for (int q = 0; q < 4; q++) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(e[2 * q], e[2 * q + 1]);
+              v0[c * 4 + q] = *reinterpret_cast<const uint32_t*>(&h2);       // in place: scores 8c.. of v0 / v1 are consumed by now
+            }
           }
         };
         if (t == 1 || g > 0) turn_wait();
-        if (full_chunk) exp_store(std::true_type{}); else exp_store(std::false_type{});
+        if (full_chunk) exp_pack(std::true_type{}); else exp_pack(std::false_type{});
         turn_pass();
-        fence_proxy_async();                                 // generic-proxy P writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        tmem_st_32x32b_x32(lane_addr + S_COL + pb * 64, v0);
+        tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(pfull(t, pb));
@@ -363,13 +362,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       //      its pfull, i.e. after this read of O: one O accumulator per tile suffices.
       mbar_wait(pvdone(t, (g - 1) & 1), (uint32_t)(((g - 1) >> 1) & 1));
       tcgen05_fence_after();
+      if (o_pending) {                                       // the previous item's O tile may still be read from the staging slice
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        o_pending = false;
+      }
       const float inv = 1.0f / l;
       // A warp's 32 rows are one batch when RB >= 32: the tile then leaves as ONE TMA store (rows >= Lq clipped by the
-      // map) staged in this warp's slice of the P buffer that PV_{g-1} has finished reading.  Otherwise per-row stores.
+      // map) staged in this warp's 4 KB slice of the tile's staging buffer.  Otherwise per-row stores.
       const int rr0 = t * 128 + (warp & 3) * 32;
       const bool warp_tma = RB >= 32 && (rr0 / RB) < it.nb;
       const bool warp_skip = RB >= 32 && !warp_tma;          // the warp's batch does not exist in this tile
-      uint8_t* stage = smem + OFF_P + (t * 2 + ((g - 1) & 1)) * P_BYTES + (warp & 3) * 4096 + lane * 128;
+      uint8_t* stage = smem + OFF_P + t * P_BYTES + (warp & 3) * 4096 + lane * 128;
       uint4* dst = reinterpret_cast<uint4*>((bf16*)p.o + (int64_t)b * p.o_bs + (int64_t)qi * p.o_rs + it.h * 64);
 #pragma unroll
       for (int hh = 0; hh < 2; hh++) {
