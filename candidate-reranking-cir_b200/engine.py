@@ -7,6 +7,7 @@ arithmetic step of the hot path is a kernel in ``csrc/``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -38,8 +39,9 @@ class Engine:
         N.check(self._lib.cir_create(C.byref(h), dev.index, N.DTYPE_BF16 if precision == "bf16" else N.DTYPE_F32), "cir_create")
         self.ctx = h
         self._ws: Optional[torch.Tensor] = None
-        self.max_triplets = 4096
-        self.max_candidates = 64
+        # stage-II chunk limits (triplets / unique candidates per cir_stage2_score call); environment overrides for sweeps
+        self.max_triplets = int(os.environ.get("CIR_MAX_TRIPLETS", 4096))
+        self.max_candidates = int(os.environ.get("CIR_MAX_CANDIDATES", 64))
 
     # ------------------------------------------------------------------ plumbing
     def _sync_stream(self):

@@ -134,3 +134,42 @@ def test_build_attn_tiles_cover():
                     assert (b0 + i, r) not in rows
                     rows.add((b0 + i, r))
         assert rows == {(t, r) for t in range(len(slot)) for r in range(L)}
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in native.py must have the size (and hence the layout rules) of the structs in
+    include/cir_b200.h: compile a tiny C program against the header and compare sizeof."""
+    import ctypes as C
+    import os
+    import subprocess
+    N = cir.native
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = {"cir_gemm_args": N.GemmArgs, "cir_gemm_ln": N.GemmLn, "cir_attn_args": N.AttnArgs, "cir_vit_weights": N.VitWeights,
+             "cir_stage1_weights": N.Stage1Weights, "cir_stage2_weights": N.Stage2Weights}
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "cir_b200.h"\nint main(void) {\n' +
+                   "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in pairs) + "  return 0;\n}\n")
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    sizes = dict(line.split() for line in out.strip().splitlines())
+    for name, ct in pairs.items():
+        assert int(sizes[name]) == C.sizeof(ct), (name, sizes[name], C.sizeof(ct))
+
+
+def test_layernorm_folding_identity():
+    """Engine._fold_ln (virtual LayerNorm): LN(x) W^T + b == rstd (x W'^T) - rstd mu colsum + b' in float64."""
+    import torch
+    g = torch.Generator().manual_seed(0)
+    K, Nn, M = 96, 40, 17
+    x = torch.randn(M, K, generator=g, dtype=torch.float64) * 1.5 + 0.4
+    W, b = torch.randn(Nn, K, generator=g, dtype=torch.float64) * 0.1, torch.randn(Nn, generator=g, dtype=torch.float64)
+    gamma, beta = 1 + 0.3 * torch.randn(K, generator=g, dtype=torch.float64), 0.2 * torch.randn(K, generator=g, dtype=torch.float64)
+    eps = 1e-12
+    want = torch.nn.functional.layer_norm(x, (K,), gamma, beta, eps) @ W.T + b
+    Wf = W * gamma[None, :]                      # (the engine rounds W' to bf16 and takes colsum of the rounded values)
+    colsum, bf = Wf.sum(1), b + W @ beta
+    mu, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
+    rstd = (var + eps).rsqrt()
+    got = rstd * (x @ Wf.T) - rstd * mu * colsum[None, :] + bf[None, :]
+    assert (got - want).abs().max() < 1e-10
