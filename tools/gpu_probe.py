@@ -1,6 +1,5 @@
 """Quick on-box performance probe (not a bench): GEMM TF/s at the path's shapes, attention time,
 stage-II chunk throughput.  Prints one line per measurement."""
-import os
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
