@@ -83,13 +83,14 @@ __device__ __noinline__ void rescale_o(uint32_t o_addr, float alpha) {
 struct Item { int batch0, nb, row0, kvrow0, h; };
 
 // work item w = head * ntiles + tile (tile fastest: CTAs running side by side share one candidate's K/V head slice in L2)
-__device__ __forceinline__ Item decode_item(const cir_attn_args& p, int w, int ntiles, int cpb) {
+__device__ __forceinline__ Item decode_item(const cir_attn_args& p, int w, int ntiles, int cpb, int RB) {
   Item it;
   it.h = w / ntiles;
   const int t = w - it.h * ntiles;
   if (p.tiles) {
     const int4 d = __ldg(reinterpret_cast<const int4*>(p.tiles) + t);
     it.batch0 = d.x; it.nb = d.y; it.row0 = d.z;
+    if (d.w != RB) { printf("cir: attention tile %d built for RB=%d, kernel geometry RB=%d (see cir_attn_args.tiles)\n", t, d.w, RB); __trap(); }
   } else {
     it.batch0 = t / cpb; it.nb = 1; it.row0 = (t - it.batch0 * cpb) * 256;
   }
@@ -165,7 +166,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   if (warp == 10) {
     // ===================== loader: TMA for Q tiles and the K / V rings =====================
     if (elect_one() && total_g > 0) {
-      auto dec = [&](int i) { return i < n_my ? decode_item(p, (int)blockIdx.x + i * (int)gridDim.x, ntiles, cpb) : Item{}; };
+      auto dec = [&](int i) { return i < n_my ? decode_item(p, (int)blockIdx.x + i * (int)gridDim.x, ntiles, cpb, RB) : Item{}; };
       // items i_cur .. i_cur+2 decoded ahead: the two dependent global loads of a decode never stall the ring
       Item it0 = dec(0), it1 = dec(1), it2 = dec(2);
       int i_cur = 0;
