@@ -21,6 +21,7 @@ struct cir_ctx {
   int prune_last;       // 1 = stage II computes the last layer for the CLS rows only (default)
   int gemm_tma_store;   // 1 = bf16 GEMM outputs leave through TMA bulk tensor stores (default)
   int virtual_ln;       // 1 = stage-II self / FFN LayerNorms are never materialised (cir_gemm_ln), when the weights carry folded copies
+  int dedup_first;      // 1 = stage II runs layer 0's query-only part once per unique query of a chunk (default)
   unsigned func_attr_mask;   // kernels whose dynamic shared-memory limit was raised on this context's device (bit per kernel)
   int fuse_ln;          // 1 = LayerNorm fused into the N=768 pair-tile GEMM epilogues where eligible (default)
   const float* ln_gamma; const float* ln_beta; float ln_eps;   // set around ONE cir_gemm call to request the fused LayerNorm

@@ -68,6 +68,7 @@ extern "C" int cir_create(cir_ctx** out, int device, int dtype) {
   c->attn_impl = 0;
   c->gemm_pair = 1;
   c->prune_last = 1;
+  c->dedup_first = 1;
   c->gemm_tma_store = 1;
   c->func_attr_mask = 0;
   c->virtual_ln = 0;
@@ -122,6 +123,7 @@ extern "C" int cir_set_attention_impl(cir_ctx* ctx, int impl) {
   return CIR_OK;
 }
 extern "C" int cir_set_prune_last_layer(cir_ctx* ctx, int enable) { ctx->prune_last = enable ? 1 : 0; return CIR_OK; }
+extern "C" int cir_set_dedup_first_layer(cir_ctx* ctx, int enable) { ctx->dedup_first = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_set_fuse_layernorm(cir_ctx* ctx, int enable) { ctx->fuse_ln = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_set_virtual_layernorm(cir_ctx* ctx, int enable) { ctx->virtual_ln = enable; return CIR_OK; }   // 1 both, 2 self-LN only, 3 FFN-LN only
 extern "C" int cir_set_gemm_tma_store(cir_ctx* ctx, int enable) { ctx->gemm_tma_store = enable ? 1 : 0; return CIR_OK; }
@@ -386,11 +388,20 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
   CIR_TRY(cir_gather_rows(ctx, gallery_tokens, cand_list, ws.cand, C, N * D));
   // stream 1 = embeddings (nlvr_encoder.py:880-886), stream 0 = z_t WITHOUT embedding LayerNorm (:892);
   // both expanded over the query's triplets (blip_stage2.py:118-124)
-  CIR_TRY(cir_bert_embeddings(ctx, ids, Q, L, w->word_emb, w->pos_emb, w->emb_ln_g, w->emb_ln_b, ws.emb));
-  CIR_TRY(cir_gather_rows(ctx, z_t, trip_query, ws.h, T, L * D));
-  CIR_TRY(cir_gather_rows(ctx, ws.emb, trip_query, at(ws.h, M * D, es), T, L * D));
-
   const int full_layers = ctx->prune_last ? CIR_LAYERS - 1 : CIR_LAYERS;
+  // The inputs of layer 0 -- and with them its whole self-attention block and its cross-attention query projection --
+  // depend on the QUERY only, not on the candidate (both streams are expanded copies, blip_stage2.py:118-124): run them
+  // once per unique query of the chunk ([2][Q*L] rows) and expand the results over the triplets.  Exact.
+  const bool dedup0 = ctx->dedup_first && full_layers >= 1 && Q <= T;
+  const int64_t Mq = Q * L;
+  if (dedup0) {
+    CIR_TRY(cir_gather_rows(ctx, z_t, nullptr, ws.h, Q, L * D));                                   // stream 0 rows of the unique queries
+    CIR_TRY(cir_bert_embeddings(ctx, ids, Q, L, w->word_emb, w->pos_emb, w->emb_ln_g, w->emb_ln_b, at(ws.h, Mq * D, es)));
+  } else {
+    CIR_TRY(cir_bert_embeddings(ctx, ids, Q, L, w->word_emb, w->pos_emb, w->emb_ln_g, w->emb_ln_b, ws.emb));
+    CIR_TRY(cir_gather_rows(ctx, z_t, trip_query, ws.h, T, L * D));
+    CIR_TRY(cir_gather_rows(ctx, ws.emb, trip_query, at(ws.h, M * D, es), T, L * D));
+  }
   // Virtual LayerNorm (cir_gemm_ln): the self-attention LayerNorm{A,B} and the FFN LayerNorm of the full layers are never
   // stored.  ws.a / ws.h then hold the RAW GEMM outputs, st1 / st3 their partial row statistics; consumers normalise
   // in their epilogues (folded weights vcq_* / vq_*), only the cross-attention LayerNorm stays a kernel.
@@ -398,6 +409,30 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
   const bool vln1 = vln && ctx->virtual_ln != 3, vln3 = vln && ctx->virtual_ln != 2;
   bool h_raw = false;                                         // ws.h = raw FFN output of the previous layer (+ st3)
   for (int i = 0; i < full_layers; i++) {                                                                          // nlvr_encoder.py:506
+    const bool per_query = dedup0 && i == 0;
+    if (per_query) {
+      // ---- layer 0, once per unique query: QKV, masked self-attention, dense + LayerNorm{A,B}, cross query projection
+      CIR_TRY(gemm(ctx, ws.h, D, Mq * D, w->self_qkv_w[0], D, 3 * D * D, w->self_qkv_b[0], 3 * D, ws.qkv, 3 * D, Mq * 3 * D, 0,
+                   nullptr, 0, 0, 0, Mq, 3 * D, D, 2, CIR_ACT_NONE));
+      for (int s = 0; s < 2; s++) {
+        cir_attn_args a{};
+        void* qkv_s = at(ws.qkv, s * Mq * 3 * D, es);
+        a.q = qkv_s; a.k = at(qkv_s, D, es); a.v = at(qkv_s, 2 * D, es); a.o = at(ws.ctx, s * Mq * D, es);
+        a.q_bs = a.k_bs = a.v_bs = L * 3 * D; a.q_rs = a.k_rs = a.v_rs = 3 * D; a.o_bs = L * D; a.o_rs = D;
+        a.key_mask = mask;                                   // mask row q belongs to query q
+        a.B = (int32_t)Q; a.H = CIR_HEADS; a.Lq = (int32_t)L; a.Lk = (int32_t)L; a.scale = 0.125f;
+        CIR_TRY(cir_attention(ctx, &a));
+      }
+      // a_q -> ws.pre, its pre-LayerNorm scratch -> ws.x, q_q -> ws.ctx (all free until the cross-attention)
+      CIR_TRY(gemm_layernorm(ctx, ws.ctx, D, Mq * D, w->self_out_w[0], D, D * D, w->self_out_b[0], D, ws.h, D, Mq * D,
+                             w->self_ln_g[0], w->self_ln_b[0], BERT_EPS, ws.x, ws.pre, Mq, D, 2));
+      CIR_TRY(gemm(ctx, ws.pre, D, Mq * D, w->cross_q_w[0], D, D * D, w->cross_q_b[0], D, ws.ctx, D, Mq * D, 0, nullptr, 0, 0, 0,
+                   Mq, D, D, 2, CIR_ACT_NONE));
+      for (int s = 0; s < 2; s++) {                           // expand over the triplets (blip_stage2.py:118-124)
+        CIR_TRY(cir_gather_rows(ctx, at(ws.pre, s * Mq * D, es), trip_query, at(ws.a, s * M * D, es), T, L * D));
+        CIR_TRY(cir_gather_rows(ctx, at(ws.ctx, s * Mq * D, es), trip_query, at(ws.qc, s * M * D, es), T, L * D));
+      }
+    } else {
     // ---- twin self-attention (:281-289, :346-363): separate weights per stream, shared padding mask (:774)
     if (h_raw) {
       cir_gemm_ln e{};
@@ -442,6 +477,7 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
       CIR_TRY(gemm(ctx, ws.a, D, M * D, w->cross_q_w[i], D, D * D, w->cross_q_b[i], D, ws.qc, D, M * D, 0, nullptr, 0, 0, 0,
                    M, D, D, 2, CIR_ACT_NONE));
     }
+    }   // !per_query
     // K/V projections once per candidate image: rows K0|V0|K1|V1 (:158-159)
     CIR_TRY(gemm(ctx, ws.cand, D, 0, w->cross_kv_w[i], D, 0, w->cross_kv_b[i], 0, ws.kv, 4 * D, 0, 0, nullptr, 0, 0, 0,
                  C * N, 4 * D, D, 1, CIR_ACT_NONE));
@@ -459,7 +495,7 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
     // m = merge(dense0(c0), dense1(c1)) folded into one K=1536 GEMM (:250-258); x_s = LayerNorm{A,B}(m + a_s) (:256,:260)
     CIR_TRY(gemm(ctx, ws.ctxc, 2 * D, 0, w->cross_out_w[i], 2 * D, 0, w->cross_out_b[i], 0, ws.m, D, 0, 0, nullptr, 0, 0, 0,
                  M, D, 2 * D, 1, CIR_ACT_NONE));
-    if (vln1) {                                                // a_s = LN(raw) on the fly from st1
+    if (vln1 && !per_query) {                                  // a_s = LN(raw) on the fly from st1
       CIR_TRY(cir_ln_cross_virtual(ctx, ws.a, ws.st1, VLN_PARTS, w->self_ln_g[i], w->self_ln_b[i], ws.m, M, w->cross_ln_g[i],
                                    w->cross_ln_b[i], M, ws.x, 2 * M, BERT_EPS));
     } else {

@@ -62,6 +62,10 @@ class Engine:
         """bf16 GEMM outputs through TMA bulk tensor stores (default on) or per-lane 16 B stores."""
         N.check(self._lib.cir_set_gemm_tma_store(self.ctx, 1 if enable else 0))
 
+    def set_dedup_first_layer(self, enable: bool):
+        """stage II: layer 0's query-only part once per unique query of a chunk (default on; exact)."""
+        N.check(self._lib.cir_set_dedup_first_layer(self.ctx, 1 if enable else 0))
+
     def set_virtual_layernorm(self, enable: bool):
         """stage II: never materialise the self-attention / FFN LayerNorms (cir_gemm_ln); bf16 only."""
         N.check(self._lib.cir_set_virtual_layernorm(self.ctx, int(enable)))

@@ -89,6 +89,7 @@ _SIGS = {
     "cir_set_gemm_impl": (C.c_int, [vp, C.c_int]),
     "cir_set_attention_impl": (C.c_int, [vp, C.c_int]),
     "cir_set_prune_last_layer": (C.c_int, [vp, C.c_int]),
+    "cir_set_dedup_first_layer": (C.c_int, [vp, C.c_int]),
     "cir_set_fuse_layernorm": (C.c_int, [vp, C.c_int]),
     "cir_set_virtual_layernorm": (C.c_int, [vp, C.c_int]),
     "cir_set_gemm_tma_store": (C.c_int, [vp, C.c_int]),

@@ -68,6 +68,9 @@ int  cir_set_gemm_impl(cir_ctx* ctx, int impl);              /* CIR_GEMM_* */
 int  cir_set_attention_impl(cir_ctx* ctx, int impl);      /* 0 auto (tcgen05 where eligible, else mma.sync), 1 CUDA-core kernel, 2 mma.sync only */
 /* stage II: compute layer 11 only for the two CLS query rows that the encoder returns (default on; 0 = all rows) */
 int  cir_set_prune_last_layer(cir_ctx* ctx, int enable);
+/* stage II: layer 0's self-attention block and cross query projection depend on the query only (both streams are expanded
+ * copies, src/blip_stage2.py:118-124): run them once per unique query of a chunk and expand (default on; exact) */
+int  cir_set_dedup_first_layer(cir_ctx* ctx, int enable);
 /* bf16 mode: fuse LayerNorm into the long-K N=768 pair-tile GEMM epilogue (FFN2): statistics in the epilogue, in-place
  * normalisation pass from L2.  Default OFF: measured 53.7k vs 54.4k triplets/s for the separate LayerNorm kernels. */
 int  cir_set_fuse_layernorm(cir_ctx* ctx, int enable);

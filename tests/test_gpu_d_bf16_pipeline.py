@@ -241,3 +241,28 @@ def test_virtual_layernorm_path(shape):
         want = torch.stack([O.stage2_score(sd2, z_ref[q:q + 1], ids[q:q + 1], mask[q:q + 1], tok_ref[cand[q].long()]) for q in range(nq)])
     err = (virt[:nq].cpu() - want).abs()
     assert err.max() <= 2e-2, (err.max(), err.mean())
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_first_layer_dedup_is_exact(precision):
+    """cir_set_dedup_first_layer: layer 0's query-only work (QKV, masked self-attention, dense + LayerNorm, cross query
+    projection) once per unique query and expanded over the triplets == the same work done per triplet."""
+    syn_ = cir.synthetic
+    sd1, sd2 = golden_weights(load_golden("pipeline_small.npz"))
+    m2 = cir.blip_stage2.blip_stage2(image_size=384, state_dict=sd2, precision=precision)
+    eng = m2.engine
+    g = torch.Generator().manual_seed(21)
+    G, Q, K, L = 5, 9, 6, 20
+    tokens = torch.randn(G, 577, 768, generator=g).cuda().to(eng.act_dtype)
+    ids, mask = syn_.make_token_ids(Q, L, seed=7, min_len=9)
+    ids[:, 0] = syn_.ENC_TOKEN_ID
+    z_t = torch.randn(Q, L, 768, generator=g).cuda().to(eng.act_dtype)
+    cand = torch.stack([torch.randint(0, G, (K,), generator=g) for _ in range(Q)]).int().numpy()
+    on = m2.score_triplets(z_t, ids, mask, tokens, cand)
+    eng.set_dedup_first_layer(False)
+    try:
+        off = m2.score_triplets(z_t, ids, mask, tokens, cand)
+    finally:
+        eng.set_dedup_first_layer(True)
+    assert torch.isfinite(on).all()
+    assert (on - off).abs().max() <= (1e-6 if precision == "fp32" else 1e-3), (on - off).abs().max()
