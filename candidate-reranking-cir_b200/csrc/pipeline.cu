@@ -519,8 +519,12 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
     // in layer 11 only the query row 0 of each stream feeds the result; its keys/values still come from all L
     // rows (self) and all N image tokens (cross).  Everything after the K/V projections runs on [2][T] rows.
     const int i = CIR_LAYERS - 1;
-    CIR_TRY(gemm(ctx, ws.h, D, M * D, w->self_qkv_w[i], D, 3 * D * D, w->self_qkv_b[i], 3 * D, ws.qkv, 3 * D, M * 3 * D, 0,
-                 nullptr, 0, 0, 0, M, 3 * D, D, 2, CIR_ACT_NONE));
+    // self K | V for all rows (weight rows 768..2303 -> qkv columns 768..2303), self Q for the CLS rows only (A row stride
+    // L*768 -> qkv row 0 of each triplet)
+    CIR_TRY(gemm(ctx, ws.h, D, M * D, at(const_cast<void*>(w->self_qkv_w[i]), D * D, es), D, 3 * D * D, w->self_qkv_b[i] + D, 3 * D,
+                 at(ws.qkv, D, es), 3 * D, M * 3 * D, 0, nullptr, 0, 0, 0, M, 2 * D, D, 2, CIR_ACT_NONE));
+    CIR_TRY(gemm(ctx, ws.h, L * D, M * D, w->self_qkv_w[i], D, 3 * D * D, w->self_qkv_b[i], 3 * D, ws.qkv, L * 3 * D, M * 3 * D, 0,
+                 nullptr, 0, 0, 0, T, D, D, 2, CIR_ACT_NONE));
     for (int s = 0; s < 2; s++) {
       cir_attn_args a{};
       void* qkv_s = at(ws.qkv, s * M * 3 * D, es);
