@@ -369,14 +369,70 @@ extern "C" size_t cir_stage2_workspace_bytes(const cir_ctx* ctx, int64_t T, int6
   return s2_plan(ctx, nullptr, 0, T, C, Q, L, N).total;
 }
 
-extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const void* gallery_tokens,
-                                const int32_t* cand_list, int64_t C, const void* z_t, const int32_t* ids,
-                                const int32_t* mask, int64_t Q, int64_t L, int64_t N,
-                                const int32_t* trip_query, const int32_t* trip_slot, int64_t T,
-                                const int32_t* attn_work, int64_t num_attn_work,
-                                const int32_t* attn_tiles, int64_t num_attn_tiles,
-                                const int32_t* attn_tiles_cls, int64_t num_attn_tiles_cls,
-                                float* scores, float* feats, void* workspace, size_t workspace_bytes) {
+// Layer 0's query-only part (both streams): QKV, masked self-attention, dense + LayerNorm{A,B} -> a_out, cross query
+// projection -> qc_out, for Q queries whose layer inputs sit in hq = [2][Q*L][768] (stream 0 = z_t, stream 1 =
+// embeddings).  qkv / ctxbuf / scratch: [2][Q*L][2304 / 768 / 768] temporaries; a_out / qc_out: [2][Q*L][768].
+static int stage2_query_block(cir_ctx* ctx, const cir_stage2_weights* w, const void* hq, const int32_t* mask, int64_t Q, int64_t L,
+                              void* qkv, void* ctxbuf, void* scratch, void* a_out, void* qc_out) {
+  const size_t es = act_size(ctx);
+  const int64_t Mq = Q * L;
+  CIR_TRY(gemm(ctx, hq, D, Mq * D, w->self_qkv_w[0], D, 3 * D * D, w->self_qkv_b[0], 3 * D, qkv, 3 * D, Mq * 3 * D, 0,
+               nullptr, 0, 0, 0, Mq, 3 * D, D, 2, CIR_ACT_NONE));
+  for (int s = 0; s < 2; s++) {
+    cir_attn_args a{};
+    void* qkv_s = at(qkv, s * Mq * 3 * D, es);
+    a.q = qkv_s; a.k = at(qkv_s, D, es); a.v = at(qkv_s, 2 * D, es); a.o = at(ctxbuf, s * Mq * D, es);
+    a.q_bs = a.k_bs = a.v_bs = L * 3 * D; a.q_rs = a.k_rs = a.v_rs = 3 * D; a.o_bs = L * D; a.o_rs = D;
+    a.key_mask = mask;                                       // mask row q belongs to query q
+    a.B = (int32_t)Q; a.H = CIR_HEADS; a.Lq = (int32_t)L; a.Lk = (int32_t)L; a.scale = 0.125f;
+    CIR_TRY(cir_attention(ctx, &a));
+  }
+  CIR_TRY(gemm_layernorm(ctx, ctxbuf, D, Mq * D, w->self_out_w[0], D, D * D, w->self_out_b[0], D, hq, D, Mq * D,
+                         w->self_ln_g[0], w->self_ln_b[0], BERT_EPS, scratch, a_out, Mq, D, 2));
+  return gemm(ctx, a_out, D, Mq * D, w->cross_q_w[0], D, D * D, w->cross_q_b[0], D, qc_out, D, Mq * D, 0, nullptr, 0, 0, 0,
+              Mq, D, D, 2, CIR_ACT_NONE);
+}
+
+// stream 0 = z_t WITHOUT embedding LayerNorm (nlvr_encoder.py:892), stream 1 = embeddings (:880-886), for Q queries
+static int stage2_query_inputs(cir_ctx* ctx, const cir_stage2_weights* w, const void* z_t, const int32_t* ids, int64_t Q, int64_t L, void* hq) {
+  CIR_TRY(cir_gather_rows(ctx, z_t, nullptr, hq, Q, L * D));
+  return cir_bert_embeddings(ctx, ids, Q, L, w->word_emb, w->pos_emb, w->emb_ln_g, w->emb_ln_b, at(hq, Q * L * D, act_size(ctx)));
+}
+
+struct S2PrefixWs { void *hq, *qkv, *ctx, *scratch; size_t total; };
+static S2PrefixWs s2_prefix_plan(const cir_ctx* ctx, void* ws, size_t bytes, int64_t Q, int64_t L) {
+  const size_t es = act_size(ctx);
+  const int64_t Mq = Q * L;
+  Bump b(ws, bytes);
+  S2PrefixWs w;
+  w.hq = b.take(2 * Mq * D * es);
+  w.qkv = b.take(2 * Mq * 3 * D * es);
+  w.ctx = b.take(2 * Mq * D * es);
+  w.scratch = b.take(2 * Mq * D * 4);
+  w.total = align_up(b.off, 256);
+  return w;
+}
+extern "C" size_t cir_stage2_prefix_workspace_bytes(const cir_ctx* ctx, int64_t Q, int64_t L) { return s2_prefix_plan(ctx, nullptr, 0, Q, L).total; }
+
+extern "C" int cir_stage2_prefix(cir_ctx* ctx, const cir_stage2_weights* w, const void* z_t, const int32_t* ids, const int32_t* mask,
+                                 int64_t Q, int64_t L, void* a0, void* qc0, void* workspace, size_t workspace_bytes) {
+  if (Q == 0) return CIR_OK;
+  CIR_CHECK_ARG(L >= 1 && L <= 512 && z_t && ids && mask && a0 && qc0, "stage2_prefix: bad argument");
+  S2PrefixWs ws = s2_prefix_plan(ctx, workspace, workspace_bytes, Q, L);
+  if (workspace_bytes < ws.total) { cir_set_error("stage2_prefix: workspace %zu < %zu", workspace_bytes, ws.total); return CIR_EWORKSPACE; }
+  CIR_TRY(stage2_query_inputs(ctx, w, z_t, ids, Q, L, ws.hq));
+  return stage2_query_block(ctx, w, ws.hq, mask, Q, L, ws.qkv, ws.ctx, ws.scratch, a0, qc0);
+}
+
+static int stage2_score_impl(cir_ctx* ctx, const cir_stage2_weights* w, const void* gallery_tokens,
+                             const int32_t* cand_list, int64_t C, const void* z_t, const int32_t* ids,
+                             const int32_t* mask, int64_t Q, int64_t L, int64_t N,
+                             const int32_t* trip_query, const int32_t* trip_slot, int64_t T,
+                             const int32_t* attn_work, int64_t num_attn_work,
+                             const int32_t* attn_tiles, int64_t num_attn_tiles,
+                             const int32_t* attn_tiles_cls, int64_t num_attn_tiles_cls,
+                             float* scores, float* feats, void* workspace, size_t workspace_bytes,
+                             const void* a0, const void* qc0) {             // optional cir_stage2_prefix results of the Q queries
   if (T == 0) return CIR_OK;
   CIR_CHECK_ARG(C >= 1 && Q >= 1, "stage2: need at least one candidate and one query");
   CIR_CHECK_ARG(L >= 1 && L <= 512 && N >= 1 && N <= 1024, "stage2: L=%lld N=%lld out of range", (long long)L, (long long)N);
@@ -392,11 +448,14 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
   // The inputs of layer 0 -- and with them its whole self-attention block and its cross-attention query projection --
   // depend on the QUERY only, not on the candidate (both streams are expanded copies, blip_stage2.py:118-124): run them
   // once per unique query of the chunk ([2][Q*L] rows) and expand the results over the triplets.  Exact.
-  const bool dedup0 = ctx->dedup_first && full_layers >= 1 && Q <= T;
+  const bool prefixed = a0 != nullptr;
+  CIR_CHECK_ARG(!prefixed || (qc0 && full_layers >= 1), "stage2: a0 and qc0 come as a pair");
+  const bool dedup0 = prefixed || (ctx->dedup_first && full_layers >= 1 && Q <= T);
   const int64_t Mq = Q * L;
-  if (dedup0) {
-    CIR_TRY(cir_gather_rows(ctx, z_t, nullptr, ws.h, Q, L * D));                                   // stream 0 rows of the unique queries
-    CIR_TRY(cir_bert_embeddings(ctx, ids, Q, L, w->word_emb, w->pos_emb, w->emb_ln_g, w->emb_ln_b, at(ws.h, Mq * D, es)));
+  if (prefixed) {
+    // nothing to prepare: layer 0 starts from the expanded a0 / qc0 rows
+  } else if (dedup0) {
+    CIR_TRY(stage2_query_inputs(ctx, w, z_t, ids, Q, L, ws.h));
   } else {
     CIR_TRY(cir_bert_embeddings(ctx, ids, Q, L, w->word_emb, w->pos_emb, w->emb_ln_g, w->emb_ln_b, ws.emb));
     CIR_TRY(cir_gather_rows(ctx, z_t, trip_query, ws.h, T, L * D));
@@ -411,26 +470,18 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
   for (int i = 0; i < full_layers; i++) {                                                                          // nlvr_encoder.py:506
     const bool per_query = dedup0 && i == 0;
     if (per_query) {
-      // ---- layer 0, once per unique query: QKV, masked self-attention, dense + LayerNorm{A,B}, cross query projection
-      CIR_TRY(gemm(ctx, ws.h, D, Mq * D, w->self_qkv_w[0], D, 3 * D * D, w->self_qkv_b[0], 3 * D, ws.qkv, 3 * D, Mq * 3 * D, 0,
-                   nullptr, 0, 0, 0, Mq, 3 * D, D, 2, CIR_ACT_NONE));
-      for (int s = 0; s < 2; s++) {
-        cir_attn_args a{};
-        void* qkv_s = at(ws.qkv, s * Mq * 3 * D, es);
-        a.q = qkv_s; a.k = at(qkv_s, D, es); a.v = at(qkv_s, 2 * D, es); a.o = at(ws.ctx, s * Mq * D, es);
-        a.q_bs = a.k_bs = a.v_bs = L * 3 * D; a.q_rs = a.k_rs = a.v_rs = 3 * D; a.o_bs = L * D; a.o_rs = D;
-        a.key_mask = mask;                                   // mask row q belongs to query q
-        a.B = (int32_t)Q; a.H = CIR_HEADS; a.Lq = (int32_t)L; a.Lk = (int32_t)L; a.scale = 0.125f;
-        CIR_TRY(cir_attention(ctx, &a));
+      // ---- layer 0, once per unique query (stage2_query_block), or precomputed for the whole query set (cir_stage2_prefix):
+      const void* a_q = a0;
+      const void* q_q = qc0;
+      if (!prefixed) {
+        // a_q -> ws.pre, its pre-LayerNorm scratch -> ws.x, q_q -> ws.qkv (written after the self-attention has read the
+        // QKV rows); all are [2][Q*L] rows and Q <= T, so the [2][T*L]-row buffers hold them
+        CIR_TRY(stage2_query_block(ctx, w, ws.h, mask, Q, L, ws.qkv, ws.ctx, ws.x, ws.pre, ws.qkv));
+        a_q = ws.pre; q_q = ws.qkv;
       }
-      // a_q -> ws.pre, its pre-LayerNorm scratch -> ws.x, q_q -> ws.ctx (all free until the cross-attention)
-      CIR_TRY(gemm_layernorm(ctx, ws.ctx, D, Mq * D, w->self_out_w[0], D, D * D, w->self_out_b[0], D, ws.h, D, Mq * D,
-                             w->self_ln_g[0], w->self_ln_b[0], BERT_EPS, ws.x, ws.pre, Mq, D, 2));
-      CIR_TRY(gemm(ctx, ws.pre, D, Mq * D, w->cross_q_w[0], D, D * D, w->cross_q_b[0], D, ws.ctx, D, Mq * D, 0, nullptr, 0, 0, 0,
-                   Mq, D, D, 2, CIR_ACT_NONE));
       for (int s = 0; s < 2; s++) {                           // expand over the triplets (blip_stage2.py:118-124)
-        CIR_TRY(cir_gather_rows(ctx, at(ws.pre, s * Mq * D, es), trip_query, at(ws.a, s * M * D, es), T, L * D));
-        CIR_TRY(cir_gather_rows(ctx, at(ws.ctx, s * Mq * D, es), trip_query, at(ws.qc, s * M * D, es), T, L * D));
+        CIR_TRY(cir_gather_rows(ctx, at(const_cast<void*>(a_q), s * Mq * D, es), trip_query, at(ws.a, s * M * D, es), T, L * D));
+        CIR_TRY(cir_gather_rows(ctx, at(const_cast<void*>(q_q), s * Mq * D, es), trip_query, at(ws.qc, s * M * D, es), T, L * D));
       }
     } else {
     // ---- twin self-attention (:281-289, :346-363): separate weights per stream, shared padding mask (:774)
@@ -563,4 +614,32 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
   CIR_TRY(gemm(ctx, ws.feats, 2 * D, 0, w->cls0_w, 2 * D, 0, w->cls0_b, 0, ws.hid, D, 0, 1, nullptr, 0, 0, 0, T, D, 2 * D, 1, CIR_ACT_RELU));
   CIR_TRY(cir_head_dot(ctx, ws.hid, w->cls2_w, w->cls2_b, scores, T));
   return CIR_OK;
+}
+
+extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const void* gallery_tokens,
+                                const int32_t* cand_list, int64_t C, const void* z_t, const int32_t* ids,
+                                const int32_t* mask, int64_t Q, int64_t L, int64_t N,
+                                const int32_t* trip_query, const int32_t* trip_slot, int64_t T,
+                                const int32_t* attn_work, int64_t num_attn_work,
+                                const int32_t* attn_tiles, int64_t num_attn_tiles,
+                                const int32_t* attn_tiles_cls, int64_t num_attn_tiles_cls,
+                                float* scores, float* feats, void* workspace, size_t workspace_bytes) {
+  CIR_CHECK_ARG(T == 0 || (z_t && ids), "stage2: z_t and ids are required");
+  return stage2_score_impl(ctx, w, gallery_tokens, cand_list, C, z_t, ids, mask, Q, L, N, trip_query, trip_slot, T, attn_work, num_attn_work,
+                           attn_tiles, num_attn_tiles, attn_tiles_cls, num_attn_tiles_cls, scores, feats, workspace, workspace_bytes,
+                           nullptr, nullptr);
+}
+
+extern "C" int cir_stage2_score_prefixed(cir_ctx* ctx, const cir_stage2_weights* w, const void* gallery_tokens,
+                                         const int32_t* cand_list, int64_t C, const void* a0, const void* qc0,
+                                         const int32_t* mask, int64_t Q, int64_t L, int64_t N,
+                                         const int32_t* trip_query, const int32_t* trip_slot, int64_t T,
+                                         const int32_t* attn_work, int64_t num_attn_work,
+                                         const int32_t* attn_tiles, int64_t num_attn_tiles,
+                                         const int32_t* attn_tiles_cls, int64_t num_attn_tiles_cls,
+                                         float* scores, float* feats, void* workspace, size_t workspace_bytes) {
+  CIR_CHECK_ARG(T == 0 || (a0 && qc0), "stage2_score_prefixed: a0 and qc0 are required");
+  return stage2_score_impl(ctx, w, gallery_tokens, cand_list, C, nullptr, nullptr, mask, Q, L, N, trip_query, trip_slot, T, attn_work,
+                           num_attn_work, attn_tiles, num_attn_tiles, attn_tiles_cls, num_attn_tiles_cls, scores, feats, workspace,
+                           workspace_bytes, a0, qc0);
 }

@@ -42,6 +42,7 @@ class Engine:
         # stage-II chunk limits (triplets / unique candidates per cir_stage2_score call); environment overrides for sweeps
         self.max_triplets = int(os.environ.get("CIR_MAX_TRIPLETS", 4096))
         self.max_candidates = int(os.environ.get("CIR_MAX_CANDIDATES", 64))
+        self.query_prefix = True       # stage2_score_matrix: layer 0's query-only part once per query set (cir_stage2_prefix)
 
     # ------------------------------------------------------------------ plumbing
     def _sync_stream(self):
@@ -328,13 +329,15 @@ class Engine:
         return out
 
     def stage2_score_chunk(self, w, gallery_tokens, cand_list, z_t, ids, mask, trip_query, trip_slot, want_feats=False,
-                           attn_work=None, attn_tiles=None, attn_tiles_cls=None):
+                           attn_work=None, attn_tiles=None, attn_tiles_cls=None, prefix=None):
         """One C-ABI call: T triplets sharing C candidates -> (scores fp32 [T], feats fp32 [T,1536] | None).
-        ``attn_work``: optional int32 [W,4] K/V-sharing work list (schedule.build_attn_work)."""
+        ``attn_work``: optional int32 [W,4] K/V-sharing work list (schedule.build_attn_work).
+        ``prefix``: optional (a0, qc0) from :meth:`stage2_prefix` for the same Q queries as ids/mask (z_t is then unused)."""
         cand_list, ids, mask = self._i32(cand_list), self._i32(ids), self._i32(mask)
         trip_query, trip_slot = self._i32(trip_query), self._i32(trip_slot)
         T, Cn, (Q, L), n_tok = trip_query.numel(), cand_list.numel(), ids.shape, gallery_tokens.shape[1]
-        assert z_t.shape == (Q, L, HIDDEN) and z_t.dtype == self.act_dtype and z_t.is_contiguous()
+        if prefix is None:
+            assert z_t.shape == (Q, L, HIDDEN) and z_t.dtype == self.act_dtype and z_t.is_contiguous()
         assert gallery_tokens.dtype == self.act_dtype and gallery_tokens.is_contiguous()
         scores = torch.empty(T, dtype=torch.float32, device=self.device)
         feats = torch.empty(T, 2 * HIDDEN, dtype=torch.float32, device=self.device) if want_feats else None
@@ -344,29 +347,55 @@ class Engine:
         at = None if attn_tiles is None or len(attn_tiles) == 0 else self._i32(attn_tiles)
         ac = None if attn_tiles_cls is None or len(attn_tiles_cls) == 0 else self._i32(attn_tiles_cls)
         self._sync_stream()
-        N.check(self._lib.cir_stage2_score(
-            self.ctx, C.byref(w), N.ptr(gallery_tokens), N.ptr(cand_list), Cn, N.ptr(z_t), N.ptr(ids), N.ptr(mask),
-            Q, L, n_tok, N.ptr(trip_query), N.ptr(trip_slot), T, N.ptr(aw), 0 if aw is None else aw.shape[0],
-            N.ptr(at), 0 if at is None else at.shape[0], N.ptr(ac), 0 if ac is None else ac.shape[0], N.ptr(scores), N.ptr(feats), N.ptr(ws), ws.numel()),
-            "cir_stage2_score")
+        tail = (Q, L, n_tok, N.ptr(trip_query), N.ptr(trip_slot), T, N.ptr(aw), 0 if aw is None else aw.shape[0],
+                N.ptr(at), 0 if at is None else at.shape[0], N.ptr(ac), 0 if ac is None else ac.shape[0], N.ptr(scores), N.ptr(feats),
+                N.ptr(ws), ws.numel())
+        if prefix is None:
+            N.check(self._lib.cir_stage2_score(self.ctx, C.byref(w), N.ptr(gallery_tokens), N.ptr(cand_list), Cn, N.ptr(z_t), N.ptr(ids),
+                                               N.ptr(mask), *tail), "cir_stage2_score")
+        else:
+            a0, qc0 = prefix
+            assert a0.shape == (2, Q * L, HIDDEN) and qc0.shape == a0.shape and a0.dtype == self.act_dtype
+            N.check(self._lib.cir_stage2_score_prefixed(self.ctx, C.byref(w), N.ptr(gallery_tokens), N.ptr(cand_list), Cn, N.ptr(a0),
+                                                        N.ptr(qc0), N.ptr(mask), *tail), "cir_stage2_score_prefixed")
         return scores, feats
+
+    def stage2_prefix(self, w, z_t, ids, mask):
+        """Layer 0's query-only part for a whole query set (cir_stage2_prefix) -> (a0, qc0), each act [2, Q*L, 768]."""
+        ids, mask = self._i32(ids), self._i32(mask)
+        Q, L = ids.shape
+        assert z_t.shape == (Q, L, HIDDEN) and z_t.dtype == self.act_dtype and z_t.is_contiguous()
+        a0 = torch.empty(2, Q * L, HIDDEN, dtype=self.act_dtype, device=self.device)
+        qc0 = torch.empty_like(a0)
+        ws = self.workspace(self._lib.cir_stage2_prefix_workspace_bytes(self.ctx, Q, L))
+        self._sync_stream()
+        N.check(self._lib.cir_stage2_prefix(self.ctx, C.byref(w), N.ptr(z_t), N.ptr(ids), N.ptr(mask), Q, L, N.ptr(a0), N.ptr(qc0),
+                                            N.ptr(ws), ws.numel()), "cir_stage2_prefix")
+        return a0, qc0
 
     def stage2_score_matrix(self, w, gallery_tokens, z_t, ids, mask, cand_idx, row_active=None):
         """All Q*K triplets, candidate-major.  z_t act [Q,L,768]; ids/mask [Q,L]; cand_idx [Q,K] ->
-        scores fp32 [Q,K]; inactive rows are filled with -99999.99 (src/validate_stage2.py:123,258)."""
+        scores fp32 [Q,K]; inactive rows are filled with -99999.99 (src/validate_stage2.py:123,258).
+        With more than one chunk, layer 0's query-only part is computed once for all Q queries (stage2_prefix) instead of
+        once per chunk for the chunk's unique queries."""
         cand_np = cand_idx.cpu().numpy() if isinstance(cand_idx, torch.Tensor) else np.asarray(cand_idx)
         Q, K = cand_np.shape
         act_np = None if row_active is None else np.asarray(row_active, dtype=bool)
         chunks = plan_chunks(cand_np, act_np, self.max_triplets, self.max_candidates)
         out = torch.full((Q * K,), NEG_FILL, dtype=torch.float32, device=self.device)
         ids_d, mask_d = self._i32(ids), self._i32(mask)
+        L = ids_d.shape[1]
+        prefix = self.stage2_prefix(w, z_t, ids_d, mask_d) if (self.query_prefix and len(chunks) > 1) else None
         for ch in chunks:
-            ql = torch.from_numpy(ch.query_list.astype(np.int64)).to(self.device)
-            s, _ = self.stage2_score_chunk(w, gallery_tokens, ch.cand_list, z_t.index_select(0, ql).contiguous(),
-                                           ids_d.index_select(0, ql), mask_d.index_select(0, ql), ch.trip_query, ch.trip_slot,
-                                           attn_work=build_attn_work(ch.trip_slot, ids_d.shape[1]),
-                                           attn_tiles=build_attn_tiles(ch.trip_slot, ids_d.shape[1]),
-                                           attn_tiles_cls=build_attn_tiles(ch.trip_slot, 1))
+            lists = dict(attn_work=build_attn_work(ch.trip_slot, L), attn_tiles=build_attn_tiles(ch.trip_slot, L),
+                         attn_tiles_cls=build_attn_tiles(ch.trip_slot, 1))
+            if prefix is not None:                              # global query rows: no per-chunk selection of z_t / ids / mask
+                s, _ = self.stage2_score_chunk(w, gallery_tokens, ch.cand_list, None, ids_d, mask_d, ch.query_list[ch.trip_query],
+                                               ch.trip_slot, prefix=prefix, **lists)
+            else:
+                ql = torch.from_numpy(ch.query_list.astype(np.int64)).to(self.device)
+                s, _ = self.stage2_score_chunk(w, gallery_tokens, ch.cand_list, z_t.index_select(0, ql).contiguous(),
+                                               ids_d.index_select(0, ql), mask_d.index_select(0, ql), ch.trip_query, ch.trip_slot, **lists)
             out.index_copy_(0, torch.from_numpy(ch.flat_pos).to(self.device), s)
         return out.view(Q, K)
 

@@ -120,6 +120,9 @@ _SIGS = {
     "cir_stage1_gallery_embed": (C.c_int, [vp, C.POINTER(Stage1Weights), vp, i64, i64, vp, vp, C.c_size_t]),
     "cir_stage2_workspace_bytes": (C.c_size_t, [vp, i64, i64, i64, i64, i64]),
     "cir_stage2_score": (C.c_int, [vp, C.POINTER(Stage2Weights), vp, vp, i64, vp, vp, vp, i64, i64, i64, vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, C.c_size_t]),
+    "cir_stage2_prefix_workspace_bytes": (C.c_size_t, [vp, i64, i64]),
+    "cir_stage2_prefix": (C.c_int, [vp, C.POINTER(Stage2Weights), vp, vp, vp, i64, i64, vp, vp, vp, C.c_size_t]),
+    "cir_stage2_score_prefixed": (C.c_int, [vp, C.POINTER(Stage2Weights), vp, vp, i64, vp, vp, vp, i64, i64, i64, vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, C.c_size_t]),
 }
 
 _lib = None

@@ -316,6 +316,22 @@ int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const void* gall
                      const int32_t* attn_tiles, int64_t num_attn_tiles,
                      const int32_t* attn_tiles_cls, int64_t num_attn_tiles_cls,
                      float* scores, float* feats, void* workspace, size_t workspace_bytes);
+/* Layer 0's query-only part for a whole query set (same arithmetic as inside cir_stage2_score, which otherwise repeats it
+ * for the unique queries of every chunk): self-attention block of both streams -> a0, cross query projection -> qc0,
+ * both act [2][Q*L][768].  Feed them to cir_stage2_score_prefixed, whose trip_query then indexes these Q rows. */
+size_t cir_stage2_prefix_workspace_bytes(const cir_ctx* ctx, int64_t Q, int64_t L);
+int cir_stage2_prefix(cir_ctx* ctx, const cir_stage2_weights* w, const void* z_t, const int32_t* ids,
+                      const int32_t* mask, int64_t Q, int64_t L, void* a0, void* qc0,
+                      void* workspace, size_t workspace_bytes);
+int cir_stage2_score_prefixed(cir_ctx* ctx, const cir_stage2_weights* w, const void* gallery_tokens,
+                              const int32_t* cand_list, int64_t C, const void* a0, const void* qc0,
+                              const int32_t* mask, int64_t Q, int64_t L, int64_t N,
+                              const int32_t* trip_query, const int32_t* trip_slot, int64_t T,
+                              const int32_t* attn_work, int64_t num_attn_work,
+                              const int32_t* attn_tiles, int64_t num_attn_tiles,
+                              const int32_t* attn_tiles_cls, int64_t num_attn_tiles_cls,
+                              float* scores, float* feats, void* workspace, size_t workspace_bytes);
+
 
 #ifdef __cplusplus
 }

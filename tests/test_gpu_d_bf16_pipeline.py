@@ -266,3 +266,33 @@ def test_first_layer_dedup_is_exact(precision):
         eng.set_dedup_first_layer(True)
     assert torch.isfinite(on).all()
     assert (on - off).abs().max() <= (1e-6 if precision == "fp32" else 1e-3), (on - off).abs().max()
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_query_prefix_is_exact(precision):
+    """cir_stage2_prefix + cir_stage2_score_prefixed (layer 0's query-only part once per query set, shared by all chunks)
+    == per-chunk computation, over several chunks."""
+    syn_ = cir.synthetic
+    sd1, sd2 = golden_weights(load_golden("pipeline_small.npz"))
+    m2 = cir.blip_stage2.blip_stage2(image_size=384, state_dict=sd2, precision=precision)
+    eng = m2.engine
+    g = torch.Generator().manual_seed(22)
+    G, Q, K, L = 7, 10, 6, 16
+    tokens = torch.randn(G, 577, 768, generator=g).cuda().to(eng.act_dtype)
+    ids, mask = syn_.make_token_ids(Q, L, seed=8, min_len=9)
+    ids[:, 0] = syn_.ENC_TOKEN_ID
+    z_t = torch.randn(Q, L, 768, generator=g).cuda().to(eng.act_dtype)
+    cand = torch.stack([torch.randperm(G, generator=g)[:K] for _ in range(Q)]).int().numpy()
+    row_active = np.ones(Q, bool)
+    row_active[3] = False
+    old = (eng.max_triplets, eng.max_candidates, eng.query_prefix)
+    eng.max_triplets, eng.max_candidates = 16, 2                       # several small chunks
+    try:
+        eng.query_prefix = True
+        a = m2.score_triplets(z_t, ids, mask, tokens, cand, row_active)
+        eng.query_prefix = False
+        b = m2.score_triplets(z_t, ids, mask, tokens, cand, row_active)
+    finally:
+        eng.max_triplets, eng.max_candidates, eng.query_prefix = old
+    assert (a[3] == cir.engine.NEG_FILL).all() and torch.isfinite(a).all()
+    assert (a - b).abs().max() <= (1e-6 if precision == "fp32" else 1e-3), (a - b).abs().max()
