@@ -12,6 +12,7 @@ hot path is made of, and stores inputs + outputs as small ``.npz`` files:
       ViT tokens (strided sample + per-image moments), stage-I gallery/query embeddings,
       stage-I top-K, z_t, stage-II 1536-d features and scores, sorted labels, recalls.
   * ``stage2_L32.npz``      -- reference-style init, Q=1, L=32 full mask, K=3 (BASELINE shape).
+  * ``training_forward.npz`` -- the in-batch B x B forward of both stages (train=True paths), B=3.
 
 The few lines of ``validate.py`` / ``validate_stage2.py`` that need datasets are restated
 inline with their file:line (they are index bookkeeping around the model calls).
@@ -92,6 +93,33 @@ def run(name, *, seed, style, G, Q, K, L, min_len, head_gain):
     print(f"{name}: {time.time() - t0:.1f}s  scores={scores.numpy().round(4).tolist()}")
 
 
+def run_training_forward(name, *, seed, style, G, B, L, min_len):
+    """In-batch (B x B) forward of both stages: BLIP_Retrieval.img_txt_fusion(train=True) (src/blip_stage1.py:67-92,
+    as called by src/stage1_train.py) and BLIP_NLVR.img_txt_fusion (src/blip_stage2.py:65-99, as called by
+    src/stage2_train.py:207,468).  Same seeded weights / images / queries as ``pipeline_small.npz``."""
+    t0 = time.time()
+    sd1 = syn.make_stage1_state_dict(seed, 384, style)
+    sd2 = syn.make_stage2_state_dict(seed, 384, style, head_gain=1.0)
+    m1, m2, tok, _ = build_models(sd1, sd2)
+    images = syn.make_images(G, 384, seed=1)
+    ref_idx, target_idx, ids, mask = syn.make_queries(B, G, L, seed=3, min_len=min_len)
+    with torch.no_grad():
+        tokens2 = m2.img_embed(images)
+        tokens1, g_emb = m1.img_embed(images, return_pool_and_normalized=True)
+        tok.push(ids, mask)
+        s1_logits = m1.img_txt_fusion(tokens1[ref_idx], g_emb[target_idx], ["x"] * B, train=True)          # [B,B] / temp
+        tok.push(ids, mask)
+        z = m1.img_txt_fusion(tokens2[ref_idx], None, ["x"] * B, train=False, return_raw=True)           # batched z_t
+        tok.push(ids, mask)
+        s2_logits = m2.img_txt_fusion(z, tokens2[target_idx], ["x"] * B, train=True)                     # [B,B]
+    np.savez_compressed(os.path.join(HERE, name), seed=seed, style=style, G=G, B=B, L=L, min_len=min_len,
+                        ref_idx=ref_idx.numpy(), target_idx=target_idx.numpy(), ids=ids.numpy(), mask=mask.numpy(),
+                        temp=float(m1.temp), s1_logits=s1_logits.numpy(), s2_logits=s2_logits.numpy(),
+                        z_t=z.last_hidden_state.numpy())
+    print(f"{name}: {time.time() - t0:.1f}s  s2_logits={s2_logits.numpy().round(4).tolist()}")
+
+
 if __name__ == "__main__":
     run("pipeline_small.npz", seed=0, style="dense", G=6, Q=3, K=4, L=12, min_len=8, head_gain=1.0)
     run("stage2_L32.npz", seed=1, style="reference", G=4, Q=1, K=3, L=32, min_len=None, head_gain=1.0)
+    run_training_forward("training_forward.npz", seed=0, style="dense", G=6, B=3, L=12, min_len=8)

@@ -126,6 +126,22 @@ def test_training_shape_forward_matches_oracle(small):
             assert (out[i].cpu() - want).abs().max() < 2e-4
 
 
+def test_training_shape_forward_matches_reference(small):
+    """Both train=True forwards against the outputs of the unmodified reference (tests/golden/training_forward.npz)."""
+    g0, m1, m2, images, tokens2 = small
+    g = load_golden("training_forward.npz")
+    tb = syn.TokenBatch(input_ids=torch.tensor(g["ids"]), attention_mask=torch.tensor(g["mask"]))
+    ref_idx, target_idx = torch.tensor(g["ref_idx"]).cuda(), torch.tensor(g["target_idx"]).cuda()
+    tokens1, g_emb = m1.img_embed(images, return_pool_and_normalized=True)
+    s1 = m1.img_txt_fusion(tokens1[ref_idx], g_emb[target_idx], tb, train=True)                 # src/blip_stage1.py:88-91
+    assert np.abs(s1.cpu().numpy() - g["s1_logits"]).max() < 1e-3                               # logits are O(1 / temp)
+    z = m1.img_txt_fusion(tokens2[ref_idx], None, tb, train=False, return_raw=True)
+    assert np.abs(z.last_hidden_state.float().cpu().numpy() - g["z_t"]).max() < 2e-4
+    s2 = m2.img_txt_fusion(z, tokens2[target_idx], tb, train=True)                             # src/blip_stage2.py:65-99
+    assert s2.shape == (int(g["B"]), int(g["B"]))
+    assert np.abs(s2.cpu().numpy() - g["s2_logits"]).max() < 2e-4
+
+
 def test_L32_reference_init(small):
     g = load_golden("stage2_L32.npz")
     sd1, sd2 = golden_weights(g)

@@ -107,3 +107,26 @@ def test_empty_positive_rows_are_filled(small):
     out = O.stage2_predictions(sd1, sd2, tokens2, torch.tensor(g["ref_idx"]), torch.tensor(g["ids"]),
                                torch.tensor(g["mask"]), torch.tensor(g["cand_idx"]), k_labels)
     assert torch.all(out == O.NEG_FILL)
+
+
+def test_training_shape_forward_matches_reference(small, golden_dir):
+    """The in-batch B x B forward of both stages (train=True paths of src/blip_stage1.py:88-91 and
+    src/blip_stage2.py:65-99) as run by the unmodified reference -> training_forward.npz."""
+    g0, sd1, sd2, images, tokens2 = small
+    g = _load(golden_dir, "training_forward.npz")
+    assert int(g["seed"]) == int(g0["seed"]) and str(g["style"]) == str(g0["style"]) and int(g["G"]) == int(g0["G"])
+    ids, mask = torch.tensor(g["ids"]), torch.tensor(g["mask"])
+    ref_idx, target_idx = torch.tensor(g["ref_idx"]), torch.tensor(g["target_idx"])
+    B = int(g["B"])
+    with torch.no_grad():
+        tokens1 = O.vit_forward(sd1, images)
+        g_emb = O.stage1_gallery_embedding(sd1, tokens1)
+        pred = O.stage1_query_embedding(sd1, O.stage1_hidden(sd1, tokens1[ref_idx], ids, mask))
+        s1 = pred @ g_emb[target_idx].T / float(sd1["temp"])
+        assert abs(float(sd1["temp"]) - float(g["temp"])) < 1e-7
+        assert np.abs(s1.numpy() - g["s1_logits"]).max() < 2e-4                     # logits are O(1/temp) = O(14)
+        z = O.stage1_hidden(sd1, tokens2[ref_idx], ids, mask)
+        assert np.abs(z.numpy() - g["z_t"]).max() < 5e-5
+        z_ref = torch.tensor(g["z_t"])
+        s2 = torch.stack([O.stage2_score(sd2, z_ref[i:i + 1], ids[i:i + 1], mask[i:i + 1], tokens2[target_idx]) for i in range(B)])
+        assert np.abs(s2.numpy() - g["s2_logits"]).max() < 1e-4
