@@ -43,6 +43,7 @@ class Engine:
         self.max_triplets = int(os.environ.get("CIR_MAX_TRIPLETS", 4096))
         self.max_candidates = int(os.environ.get("CIR_MAX_CANDIDATES", 64))
         self.query_prefix = True       # stage2_score_matrix: layer 0's query-only part once per query set (cir_stage2_prefix)
+        self.prefix_batch = 8192       # queries per cir_stage2_prefix call (bounds its workspace: ~0.7 MB per query at L = 32)
 
     # ------------------------------------------------------------------ plumbing
     def _sync_stream(self):
@@ -360,17 +361,27 @@ class Engine:
                                                         N.ptr(qc0), N.ptr(mask), *tail), "cir_stage2_score_prefixed")
         return scores, feats
 
-    def stage2_prefix(self, w, z_t, ids, mask):
-        """Layer 0's query-only part for a whole query set (cir_stage2_prefix) -> (a0, qc0), each act [2, Q*L, 768]."""
+    def stage2_prefix(self, w, z_t, ids, mask, batch: Optional[int] = None):
+        """Layer 0's query-only part for a whole query set (cir_stage2_prefix) -> (a0, qc0), each act [2, Q*L, 768].
+        Query sets larger than ``batch`` (default ``self.prefix_batch``) go through several calls to bound the workspace."""
         ids, mask = self._i32(ids), self._i32(mask)
         Q, L = ids.shape
         assert z_t.shape == (Q, L, HIDDEN) and z_t.dtype == self.act_dtype and z_t.is_contiguous()
+        batch = self.prefix_batch if batch is None else batch
         a0 = torch.empty(2, Q * L, HIDDEN, dtype=self.act_dtype, device=self.device)
         qc0 = torch.empty_like(a0)
-        ws = self.workspace(self._lib.cir_stage2_prefix_workspace_bytes(self.ctx, Q, L))
         self._sync_stream()
-        N.check(self._lib.cir_stage2_prefix(self.ctx, C.byref(w), N.ptr(z_t), N.ptr(ids), N.ptr(mask), Q, L, N.ptr(a0), N.ptr(qc0),
-                                            N.ptr(ws), ws.numel()), "cir_stage2_prefix")
+        for q0 in range(0, Q, batch):
+            nb = min(batch, Q - q0)
+            whole = nb == Q
+            a_b = a0 if whole else torch.empty(2, nb * L, HIDDEN, dtype=self.act_dtype, device=self.device)
+            q_b = qc0 if whole else torch.empty_like(a_b)
+            ws = self.workspace(self._lib.cir_stage2_prefix_workspace_bytes(self.ctx, nb, L))
+            N.check(self._lib.cir_stage2_prefix(self.ctx, C.byref(w), N.ptr(z_t[q0:q0 + nb]), N.ptr(ids[q0:q0 + nb]), N.ptr(mask[q0:q0 + nb]),
+                                                nb, L, N.ptr(a_b), N.ptr(q_b), N.ptr(ws), ws.numel()), "cir_stage2_prefix")
+            if not whole:
+                a0[:, q0 * L:(q0 + nb) * L].copy_(a_b)
+                qc0[:, q0 * L:(q0 + nb) * L].copy_(q_b)
         return a0, qc0
 
     def stage2_score_matrix(self, w, gallery_tokens, z_t, ids, mask, cand_idx, row_active=None):

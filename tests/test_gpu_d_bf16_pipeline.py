@@ -285,14 +285,14 @@ def test_query_prefix_is_exact(precision):
     cand = torch.stack([torch.randperm(G, generator=g)[:K] for _ in range(Q)]).int().numpy()
     row_active = np.ones(Q, bool)
     row_active[3] = False
-    old = (eng.max_triplets, eng.max_candidates, eng.query_prefix)
-    eng.max_triplets, eng.max_candidates = 16, 2                       # several small chunks
+    old = (eng.max_triplets, eng.max_candidates, eng.query_prefix, eng.prefix_batch)
+    eng.max_triplets, eng.max_candidates, eng.prefix_batch = 16, 2, 4   # several small chunks, prefix in 3 calls
     try:
         eng.query_prefix = True
         a = m2.score_triplets(z_t, ids, mask, tokens, cand, row_active)
         eng.query_prefix = False
         b = m2.score_triplets(z_t, ids, mask, tokens, cand, row_active)
     finally:
-        eng.max_triplets, eng.max_candidates, eng.query_prefix = old
+        eng.max_triplets, eng.max_candidates, eng.query_prefix, eng.prefix_batch = old
     assert (a[3] == cir.engine.NEG_FILL).all() and torch.isfinite(a).all()
     assert (a - b).abs().max() <= (1e-6 if precision == "fp32" else 1e-3), (a - b).abs().max()
