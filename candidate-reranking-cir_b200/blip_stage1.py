@@ -14,13 +14,15 @@ from .engine import Engine, get_engine
 class BLIP_Retrieval(nn.Module):
     def __init__(self, med_config="configs/med_config.json", image_size=384, vit="base", vit_grad_ckpt=False,
                  vit_ckpt_layer=0, embed_dim=256, *, state_dict: Optional[Dict[str, torch.Tensor]] = None,
-                 precision: str = "bf16", device=None, engine: Optional[Engine] = None):
+                 precision: str = "bf16", device=None, engine: Optional[Engine] = None,
+                 synthetic_tokenizer: bool = False):
         super().__init__()
         check_vit(vit)
         assert embed_dim == 256, "embed_dim is fixed at 256 (src/blip_stage1.py:22)"
         self.image_size = image_size
         self.engine = engine or get_engine(device, precision)
-        self.tokenizer = init_tokenizer()
+        self.tokenizer = init_tokenizer(synthetic_tokenizer)
+        self._from_checkpoint = False
         self.temp = 0.07
         self._vit = self._w = None
         self._keep = []
@@ -86,5 +88,10 @@ def blip_stage1(pretrained="", **kwargs):
     model = BLIP_Retrieval(**kwargs)
     if pretrained:
         from .checkpoint import load_state_dict
+        from .synthetic import SyntheticTokenizer
+        if isinstance(model.tokenizer, SyntheticTokenizer):
+            raise N.CirError("a real checkpoint needs the real BERT WordPiece tokenizer: the synthetic hash tokenizer is for "
+                             "synthetic weights only (assign model.tokenizer or pass pre-tokenised batches)")
         model.load_state_dict(load_state_dict(pretrained, "BLIP_Retrieval", kwargs.get("image_size", model.image_size)))
+        model._from_checkpoint = True
     return model

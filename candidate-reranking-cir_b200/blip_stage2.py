@@ -15,7 +15,8 @@ from .engine import Engine, get_engine
 class BLIP_NLVR(nn.Module):
     def __init__(self, med_config="configs/med_config.json", image_size=480, vit="base", vit_grad_ckpt=False,
                  vit_ckpt_layer=0, *, state_dict: Optional[Dict[str, torch.Tensor]] = None, precision: str = "bf16",
-                 device=None, engine: Optional[Engine] = None):
+                 device=None, engine: Optional[Engine] = None,
+                 synthetic_tokenizer: bool = False):
         """Signature of src/blip_stage2.py:20-26 plus keyword-only extras: ``state_dict`` (reference
         key names), ``precision`` ("bf16" | "fp32" check mode), ``device``/``engine``.
         ``med_config`` is accepted for compatibility; the dims are the fixed BERT-base/ViT-B ones of
@@ -24,7 +25,8 @@ class BLIP_NLVR(nn.Module):
         check_vit(vit)
         self.image_size = image_size
         self.engine = engine or get_engine(device, precision)
-        self.tokenizer = init_tokenizer()
+        self.tokenizer = init_tokenizer(synthetic_tokenizer)
+        self._from_checkpoint = False
         self._vit = self._w = None
         self._keep = []
         if state_dict is not None:
@@ -97,5 +99,10 @@ def blip_stage2(pretrained="", **kwargs):
     model = BLIP_NLVR(**kwargs)
     if pretrained:
         from .checkpoint import load_state_dict
+        from .synthetic import SyntheticTokenizer
+        if isinstance(model.tokenizer, SyntheticTokenizer):
+            raise N.CirError("a real checkpoint needs the real BERT WordPiece tokenizer: the synthetic hash tokenizer is for "
+                             "synthetic weights only (assign model.tokenizer or pass pre-tokenised batches)")
         model.load_state_dict(load_state_dict(pretrained, "BLIP_NLVR", kwargs.get("image_size", model.image_size)))
+        model._from_checkpoint = True
     return model

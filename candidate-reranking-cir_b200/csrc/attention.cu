@@ -439,6 +439,7 @@ size_t simt_smem_bytes(int Lk) {
 }  // namespace
 
 extern "C" int cir_attention(cir_ctx* ctx, const cir_attn_args* a) {
+  CIR_ENTER(ctx);
   if (a->B == 0 || a->Lq == 0) return CIR_OK;
   CIR_CHECK_ARG(a->Lk >= 1 && a->Lk <= 1024, "attention: Lk=%d out of range [1,1024]", a->Lk);
   CIR_CHECK_ARG(a->H >= 1 && a->H <= 65535, "attention: bad head count %d", a->H);

@@ -65,6 +65,17 @@ void cir_set_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
+// Every C-ABI entry point that touches the device runs on ctx->device and puts the caller's current device back on exit
+// (two contexts on different GPUs may be driven from one thread).
+struct CirDeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit CirDeviceGuard(int want) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != want) switched = cudaSetDevice(want) == cudaSuccess;
+  }
+  ~CirDeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define CIR_ENTER(ctx) CirDeviceGuard cir_device_guard__((ctx)->device)
+
 #define CIR_TRY(call)            \
   do {                           \
     int r__ = (call);            \

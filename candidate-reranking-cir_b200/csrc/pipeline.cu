@@ -60,7 +60,8 @@ extern "C" int cir_create(cir_ctx** out, int device, int dtype) {
     cir_set_error("cir_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
     return CIR_EUNSUPPORTED;
   }
-  CIR_CUDA(cudaSetDevice(device));
+  CirDeviceGuard guard(device);      // initialise the device's primary context without changing the caller's current device
+  CIR_CUDA(cudaFree(0));
   cir_ctx* c = new cir_ctx();
   c->device = device;
   c->dtype = dtype;
@@ -98,6 +99,7 @@ extern "C" int cir_profile_gemm(cir_ctx* ctx, int enable) {
   return CIR_OK;
 }
 extern "C" int cir_profile_gemm_read(cir_ctx* ctx, double* total_ms, double* total_flops, int64_t* launches) {
+  CIR_ENTER(ctx);
   ProfState* ps = (ProfState*)ctx->prof;
   double ms = 0.0, fl = 0.0;
   for (size_t i = 0; i < ps->used; i++) {
@@ -135,6 +137,7 @@ extern "C" int64_t cir_launch_count(cir_ctx* ctx, int reset) {
 }
 
 extern "C" int cir_gemm(cir_ctx* ctx, const cir_gemm_args* a) {
+  CIR_ENTER(ctx);
   CIR_CHECK_ARG(a && a->A && a->W && a->C, "gemm: null operand");
   CIR_CHECK_ARG(a->M >= 0 && a->N >= 0 && a->K > 0 && a->batch >= 0, "gemm: bad shape M=%lld N=%lld K=%lld", (long long)a->M, (long long)a->N, (long long)a->K);
   const bool tc = ctx->dtype == CIR_DTYPE_BF16 && ctx->gemm_impl != CIR_GEMM_SIMT;
@@ -223,6 +226,7 @@ extern "C" size_t cir_vit_workspace_bytes(const cir_ctx* ctx, int64_t B, int64_t
 
 extern "C" int cir_vit_forward(cir_ctx* ctx, const cir_vit_weights* w, const float* images, int64_t B,
                                int64_t S, void* tokens, void* workspace, size_t workspace_bytes) {
+  CIR_ENTER(ctx);
   if (B == 0) return CIR_OK;
   CIR_CHECK_ARG(S % 16 == 0 && S >= 16, "vit: image size %lld is not a multiple of 16", (long long)S);
   VitWs ws = vit_plan(ctx, workspace, workspace_bytes, B, S);
@@ -292,6 +296,7 @@ extern "C" int cir_stage1_encode(cir_ctx* ctx, const cir_stage1_weights* w, cons
                                  const int32_t* ref_index, const int32_t* ids, const int32_t* mask,
                                  int64_t Q, int64_t L, int64_t N, void* z_t, float* q_emb, int normalize_twice,
                                  void* workspace, size_t workspace_bytes) {
+  CIR_ENTER(ctx);
   if (Q == 0) return CIR_OK;
   CIR_CHECK_ARG(L >= 1 && L <= 512 && N >= 1 && N <= 1024, "stage1: L=%lld N=%lld out of range", (long long)L, (long long)N);
   S1Ws ws = s1_plan(ctx, workspace, workspace_bytes, Q, L, N);
@@ -331,6 +336,7 @@ extern "C" int cir_stage1_encode(cir_ctx* ctx, const cir_stage1_weights* w, cons
 
 extern "C" int cir_stage1_gallery_embed(cir_ctx* ctx, const cir_stage1_weights* w, const void* tokens, int64_t G,
                                         int64_t N, float* g_emb, void* workspace, size_t workspace_bytes) {
+  CIR_ENTER(ctx);
   if (G == 0) return CIR_OK;
   const size_t need = align_up((size_t)G * CIR_EMBED * 4, 256);
   if (workspace_bytes < need) { cir_set_error("gallery_embed: workspace %zu < %zu", workspace_bytes, need); return CIR_EWORKSPACE; }
@@ -416,6 +422,7 @@ extern "C" size_t cir_stage2_prefix_workspace_bytes(const cir_ctx* ctx, int64_t 
 
 extern "C" int cir_stage2_prefix(cir_ctx* ctx, const cir_stage2_weights* w, const void* z_t, const int32_t* ids, const int32_t* mask,
                                  int64_t Q, int64_t L, void* a0, void* qc0, void* workspace, size_t workspace_bytes) {
+  CIR_ENTER(ctx);
   if (Q == 0) return CIR_OK;
   CIR_CHECK_ARG(L >= 1 && L <= 512 && z_t && ids && mask && a0 && qc0, "stage2_prefix: bad argument");
   S2PrefixWs ws = s2_prefix_plan(ctx, workspace, workspace_bytes, Q, L);
@@ -624,6 +631,7 @@ extern "C" int cir_stage2_score(cir_ctx* ctx, const cir_stage2_weights* w, const
                                 const int32_t* attn_tiles, int64_t num_attn_tiles,
                                 const int32_t* attn_tiles_cls, int64_t num_attn_tiles_cls,
                                 float* scores, float* feats, void* workspace, size_t workspace_bytes) {
+  CIR_ENTER(ctx);
   CIR_CHECK_ARG(T == 0 || (z_t && ids), "stage2: z_t and ids are required");
   return stage2_score_impl(ctx, w, gallery_tokens, cand_list, C, z_t, ids, mask, Q, L, N, trip_query, trip_slot, T, attn_work, num_attn_work,
                            attn_tiles, num_attn_tiles, attn_tiles_cls, num_attn_tiles_cls, scores, feats, workspace, workspace_bytes,
@@ -638,6 +646,7 @@ extern "C" int cir_stage2_score_prefixed(cir_ctx* ctx, const cir_stage2_weights*
                                          const int32_t* attn_tiles, int64_t num_attn_tiles,
                                          const int32_t* attn_tiles_cls, int64_t num_attn_tiles_cls,
                                          float* scores, float* feats, void* workspace, size_t workspace_bytes) {
+  CIR_ENTER(ctx);
   CIR_CHECK_ARG(T == 0 || (a0 && qc0), "stage2_score_prefixed: a0 and qc0 are required");
   return stage2_score_impl(ctx, w, gallery_tokens, cand_list, C, nullptr, nullptr, mask, Q, L, N, trip_query, trip_slot, T, attn_work,
                            num_attn_work, attn_tiles, num_attn_tiles, attn_tiles_cls, num_attn_tiles_cls, scores, feats, workspace,

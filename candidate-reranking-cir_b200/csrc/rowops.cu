@@ -222,6 +222,7 @@ inline unsigned flat_blocks(int64_t n, int threads = 256) {
 extern "C" int cir_add_layernorm(cir_ctx* ctx, const void* x, int x_f32, int64_t x_rows, const void* res,
                                  const float* gamma, const float* beta, int64_t rows_per_group,
                                  void* y, int y_f32, int64_t rows, float eps) {
+  CIR_ENTER(ctx);
   if (rows == 0) return CIR_OK;
   CIR_CHECK_ARG(x && gamma && beta && y && x_rows > 0 && rows_per_group > 0, "add_layernorm: null/zero argument");
   const bool f32 = ctx->dtype == CIR_DTYPE_F32;
@@ -251,6 +252,7 @@ int cir_ln_cross_virtual(cir_ctx* ctx, const void* raw, const float* stats, int 
 
 extern "C" int cir_bert_embeddings(cir_ctx* ctx, const int32_t* ids, int64_t Q, int64_t L, const float* word_emb,
                                    const float* pos_emb, const float* gamma, const float* beta, void* out) {
+  CIR_ENTER(ctx);
   const int64_t rows = Q * L;
   if (rows == 0) return CIR_OK;
   CIR_CHECK_ARG(L <= 512, "bert_embeddings: L=%lld exceeds max_position_embeddings 512", (long long)L);
@@ -263,6 +265,7 @@ extern "C" int cir_bert_embeddings(cir_ctx* ctx, const int32_t* ids, int64_t Q, 
 }
 
 extern "C" int cir_gather_rows(cir_ctx* ctx, const void* src, const int32_t* index, void* dst, int64_t rows, int64_t row_elems) {
+  CIR_ENTER(ctx);
   if (rows == 0 || row_elems == 0) return CIR_OK;
   const int64_t row_bytes = row_elems * (int64_t)act_size(ctx);
   CIR_CHECK_ARG(row_bytes % 16 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "gather_rows: rows must be 16 B multiples and aligned");
@@ -273,6 +276,7 @@ extern "C" int cir_gather_rows(cir_ctx* ctx, const void* src, const int32_t* ind
 }
 
 extern "C" int cir_cast_f32_to_act(cir_ctx* ctx, const float* src, void* dst, int64_t n) {
+  CIR_ENTER(ctx);
   if (n == 0) return CIR_OK;
   if (ctx->dtype == CIR_DTYPE_F32) cast_kernel<float, float><<<flat_blocks(n), 256, 0, ctx->stream>>>(src, (float*)dst, n);
   else cast_kernel<float, bf16><<<flat_blocks(n), 256, 0, ctx->stream>>>(src, (bf16*)dst, n);
@@ -281,6 +285,7 @@ extern "C" int cir_cast_f32_to_act(cir_ctx* ctx, const float* src, void* dst, in
 }
 
 extern "C" int cir_cast_act_to_f32(cir_ctx* ctx, const void* src, float* dst, int64_t n) {
+  CIR_ENTER(ctx);
   if (n == 0) return CIR_OK;
   if (ctx->dtype == CIR_DTYPE_F32) cast_kernel<float, float><<<flat_blocks(n), 256, 0, ctx->stream>>>((const float*)src, dst, n);
   else cast_kernel<bf16, float><<<flat_blocks(n), 256, 0, ctx->stream>>>((const bf16*)src, dst, n);
@@ -289,6 +294,7 @@ extern "C" int cir_cast_act_to_f32(cir_ctx* ctx, const void* src, float* dst, in
 }
 
 extern "C" int cir_l2_normalize(cir_ctx* ctx, const float* x, float* y, int64_t rows, int64_t dim) {
+  CIR_ENTER(ctx);
   if (rows == 0) return CIR_OK;
   l2_normalize_kernel<<<row_blocks(rows), WARPS * 32, 0, ctx->stream>>>(x, y, rows, dim);
   CIR_LAUNCH_CHECK(ctx);

@@ -148,11 +148,40 @@ __global__ void recall_counts_kernel(const uint8_t* __restrict__ labels, const i
   }
 }
 
+// One thread per query: fp32 distances 1 - q . g[member] of P <= 32 named gallery rows (the dot product accumulates k = 0..255 in
+// order with fmaf, exactly like the similarity tiles of cir_stage1_topk), then the members' slots ranked by (distance, gallery index).
+__global__ void rank_members_kernel(const float* __restrict__ q_emb, const float* __restrict__ g_emb, const int32_t* __restrict__ members,
+                                    int64_t Q, int P, float* __restrict__ out_dist, int32_t* __restrict__ out_order) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  uint64_t keys[32];
+  const float4* qv = reinterpret_cast<const float4*>(q_emb + q * CIR_EMBED);
+  for (int j = 0; j < P; j++) {
+    const int32_t gi = members[q * P + j];
+    const float4* gv = reinterpret_cast<const float4*>(g_emb + (int64_t)gi * CIR_EMBED);
+    float acc = 0.f;
+    for (int k = 0; k < CIR_EMBED / 4; k++) {
+      const float4 a = qv[k], b = __ldg(gv + k);
+      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    }
+    const float d = 1.0f - acc;
+    out_dist[q * P + j] = d;
+    keys[j] = ((uint64_t)ordered_bits(d) << 32) | (uint32_t)gi;
+  }
+  // rank r of slot j = number of members with a smaller key (equal gallery rows keep slot order)
+  for (int j = 0; j < P; j++) {
+    int r = 0;
+    for (int i = 0; i < P; i++) r += (keys[i] < keys[j]) || (keys[i] == keys[j] && i < j);
+    out_order[q * P + r] = j;
+  }
+}
+
 inline int pow2_at_least(int64_t k) { int p = 1; while (p < k) p <<= 1; return p; }
 
 }  // namespace
 
 extern "C" int cir_rerank_sort(cir_ctx* ctx, const float* scores, int64_t Q, int64_t K, int32_t* order) {
+  CIR_ENTER(ctx);
   if (Q == 0 || K == 0) return CIR_OK;
   CIR_CHECK_ARG(K <= 2048, "rerank_sort: K=%lld > 2048", (long long)K);
   const int n_pad = pow2_at_least(K);
@@ -169,6 +198,7 @@ extern "C" size_t cir_topk_workspace_bytes(int64_t Q, int64_t G, int64_t K) {
 extern "C" int cir_topk_from_dist(cir_ctx* ctx, const float* dist, int64_t Q, int64_t G, int64_t ldd,
                                   const int32_t* exclude, int64_t col_offset, int64_t K,
                                   float* top_dist, int32_t* top_idx, void* workspace, size_t workspace_bytes) {
+  CIR_ENTER(ctx);
   if (Q == 0) return CIR_OK;
   CIR_CHECK_ARG(K >= 1 && K <= MAXK, "topk: K=%lld out of range [1,%d]", (long long)K, MAXK);
   if (workspace_bytes < cir_topk_workspace_bytes(Q, G, K)) { cir_set_error("topk: workspace too small"); return CIR_EWORKSPACE; }
@@ -191,6 +221,7 @@ extern "C" size_t cir_stage1_topk_workspace_bytes(int64_t Q, int64_t G, int64_t 
 extern "C" int cir_stage1_topk(cir_ctx* ctx, const float* q_emb, const float* g_emb, int64_t Q, int64_t G,
                                const int32_t* exclude, int64_t col_offset, int64_t K,
                                float* top_dist, int32_t* top_idx, void* workspace, size_t workspace_bytes) {
+  CIR_ENTER(ctx);
   if (Q == 0) return CIR_OK;
   CIR_CHECK_ARG(K >= 1 && K <= MAXK, "stage1_topk: K=%lld out of range [1,%d]", (long long)K, MAXK);
   if (workspace_bytes < cir_stage1_topk_workspace_bytes(Q, G, K)) { cir_set_error("stage1_topk: workspace too small"); return CIR_EWORKSPACE; }
@@ -228,6 +259,7 @@ __global__ void divide_rows_kernel(float* __restrict__ x, int64_t n, float d) {
 }
 
 extern "C" int cir_stage1_logits(cir_ctx* ctx, const float* q_emb, const float* t_emb, int64_t Q, int64_t G, float temp, float* logits) {
+  CIR_ENTER(ctx);
   if (Q == 0 || G == 0) return CIR_OK;
   CIR_CHECK_ARG(temp != 0.f, "stage1_logits: temp must be non-zero");
   cir_gemm_args ga{};
@@ -242,8 +274,20 @@ extern "C" int cir_stage1_logits(cir_ctx* ctx, const float* q_emb, const float* 
   return CIR_OK;
 }
 
+extern "C" int cir_stage1_rank_members(cir_ctx* ctx, const float* q_emb, const float* g_emb, const int32_t* members, int64_t Q,
+                                       int64_t P, float* member_dist, int32_t* member_order) {
+  CIR_ENTER(ctx);
+  if (Q == 0 || P == 0) return CIR_OK;
+  CIR_CHECK_ARG(P >= 1 && P <= 32, "rank_members: P=%lld out of range [1,32]", (long long)P);
+  CIR_CHECK_ARG(q_emb && g_emb && members && member_dist && member_order, "rank_members: null argument");
+  rank_members_kernel<<<(unsigned)((Q + 127) / 128), 128, 0, ctx->stream>>>(q_emb, g_emb, members, Q, (int)P, member_dist, member_order);
+  CIR_LAUNCH_CHECK(ctx);
+  return CIR_OK;
+}
+
 extern "C" int cir_topk_merge(cir_ctx* ctx, const float* dist_in, const int32_t* idx_in, int64_t P, int64_t Q,
                               int64_t K, float* top_dist, int32_t* top_idx, void* workspace, size_t workspace_bytes) {
+  CIR_ENTER(ctx);
   if (Q == 0 || P == 0) return CIR_OK;
   CIR_CHECK_ARG(K >= 1 && K <= MAXK, "topk_merge: K=%lld out of range", (long long)K);
   if (workspace_bytes < cir_topk_workspace_bytes(Q, 0, K)) { cir_set_error("topk_merge: workspace too small"); return CIR_EWORKSPACE; }
@@ -261,6 +305,7 @@ extern "C" int cir_topk_merge(cir_ctx* ctx, const float* dist_in, const int32_t*
 
 extern "C" int cir_recall_counts(cir_ctx* ctx, const uint8_t* labels, const int32_t* order, int64_t Q, int64_t K,
                                  const int32_t* ks_host, int32_t num_ks, int64_t* hits) {
+  CIR_ENTER(ctx);
   CIR_CHECK_ARG(num_ks >= 1 && num_ks <= 16, "recall_counts: num_ks=%d out of range [1,16]", num_ks);
   RecallParams rp{};
   rp.num = num_ks;

@@ -116,6 +116,25 @@ class Engine:
         N.check(self._lib.cir_cast_act_to_f32(self.ctx, N.ptr(t.contiguous()), N.ptr(out), t.numel()), "cast")
         return out
 
+    def _check_range(self, a, hi: int, what: str):
+        """Host-resident index arrays are range-checked before they reach a device gather (the kernels trust them);
+        device-resident ones only with ``CIR_CHECK_INDICES=1`` (it costs a stream synchronisation)."""
+        if hi is None:
+            return
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda and os.environ.get("CIR_CHECK_INDICES") != "1":
+                return
+            if a.numel() == 0:
+                return
+            lo_v, hi_v = int(a.min()), int(a.max())
+        else:
+            a = np.asarray(a)
+            if a.size == 0:
+                return
+            lo_v, hi_v = int(a.min()), int(a.max())
+        if lo_v < 0 or hi_v >= hi:
+            raise N.CirError(f"{what}: index range [{lo_v}, {hi_v}] outside [0, {hi}) -- stale top-K file, wrong gallery or wrong tokenizer?")
+
     def _i32(self, a) -> torch.Tensor:
         if isinstance(a, torch.Tensor):
             return a.to(device=self.device, dtype=torch.int32).contiguous()
@@ -164,6 +183,7 @@ class Engine:
         w = N.Stage1Weights()
         e = "text_encoder.embeddings."
         w.word_emb = self._cat_p(sd, [e + "word_embeddings.weight"], keep)
+        self.vocab_rows = int(sd[e + "word_embeddings.weight"].shape[0])
         w.pos_emb = self._cat_p(sd, [e + "position_embeddings.weight"], keep)
         w.emb_ln_g = self._cat_p(sd, [e + "LayerNorm.weight"], keep)
         w.emb_ln_b = self._cat_p(sd, [e + "LayerNorm.bias"], keep)
@@ -203,6 +223,7 @@ class Engine:
         w = N.Stage2Weights()
         e = "text_encoder.embeddings."
         w.word_emb = self._cat_p(sd, [e + "word_embeddings.weight"], keep)
+        self.vocab_rows = int(sd[e + "word_embeddings.weight"].shape[0])
         w.pos_emb = self._cat_p(sd, [e + "position_embeddings.weight"], keep)
         w.emb_ln_g = self._cat_p(sd, [e + "LayerNorm.weight"], keep)
         w.emb_ln_b = self._cat_p(sd, [e + "LayerNorm.bias"], keep)
@@ -223,6 +244,10 @@ class Engine:
                                                c + "self1.key.bias", c + "self1.value.bias"], keep)
             W0, W1 = sd[c + "output.dense0.weight"].double(), sd[c + "output.dense1.weight"].double()
             b0, b1 = sd[c + "output.dense0.bias"].double(), sd[c + "output.dense1.bias"].double()
+            if i >= 6 and c + "output.merge_layer.weight" not in sd:
+                raise N.CirError(f"state_dict has no {c}output.merge_layer.*: a BLIP base checkpoint carries no trained merge "
+                                 "layers (the reference would leave them randomly initialised, src/blip_stage2.py:188-191); "
+                                 "stage II needs a fine-tuned BLIP_NLVR checkpoint")
             if i >= 6:      # mergeMLP: merge_layer(cat[dense0(c0), dense1(c1)]), no activation (:252-254)
                 Wm, bm = sd[c + "output.merge_layer.weight"].double(), sd[c + "output.merge_layer.bias"].double()
                 Wa, Wb = Wm[:, :HIDDEN], Wm[:, HIDDEN:]
@@ -302,6 +327,8 @@ class Engine:
     def stage1_encode(self, w, gallery_tokens: torch.Tensor, ref_index, ids, mask, want_z=True, want_emb=True,
                       normalize_twice=False, batch: int = 256):
         """-> (z_t act [Q,L,768] | None, q_emb fp32 [Q,256] | None)"""
+        self._check_range(ref_index, gallery_tokens.shape[0], "stage1_encode ref_index")
+        self._check_range(ids, getattr(self, "vocab_rows", None), "stage1_encode token ids")
         ref_index, ids, mask = self._i32(ref_index), self._i32(ids), self._i32(mask)
         Q, L = ids.shape
         n_tok = gallery_tokens.shape[1]
@@ -391,6 +418,8 @@ class Engine:
         once per chunk for the chunk's unique queries."""
         cand_np = cand_idx.cpu().numpy() if isinstance(cand_idx, torch.Tensor) else np.asarray(cand_idx)
         Q, K = cand_np.shape
+        self._check_range(cand_np, gallery_tokens.shape[0], "stage2_score_matrix cand_idx")
+        self._check_range(ids, getattr(self, "vocab_rows", None), "stage2_score_matrix token ids")
         act_np = None if row_active is None else np.asarray(row_active, dtype=bool)
         chunks = plan_chunks(cand_np, act_np, self.max_triplets, self.max_candidates)
         out = torch.full((Q * K,), NEG_FILL, dtype=torch.float32, device=self.device)
@@ -443,6 +472,20 @@ class Engine:
         N.check(self._lib.cir_stage1_topk(self.ctx, N.ptr(q_emb), N.ptr(g_emb), Q, G, N.ptr(ex), col_offset, k, N.ptr(td),
                                           N.ptr(ti), N.ptr(ws), ws.numel()), "cir_stage1_topk")
         return td, ti
+
+    def stage1_rank_members(self, q_emb: torch.Tensor, g_emb: torch.Tensor, members):
+        """members int [Q,P] gallery rows -> (dist fp32 [Q,P], order int32 [Q,P]: slot of the r-th closest member)."""
+        q_emb = q_emb.to(self.device, torch.float32).contiguous()
+        g_emb = g_emb.to(self.device, torch.float32).contiguous()
+        self._check_range(members, g_emb.shape[0], "stage1_rank_members")
+        mem = self._i32(members)
+        Q, P = mem.shape
+        md = torch.empty(Q, P, dtype=torch.float32, device=self.device)
+        mo = torch.empty(Q, P, dtype=torch.int32, device=self.device)
+        self._sync_stream()
+        N.check(self._lib.cir_stage1_rank_members(self.ctx, N.ptr(q_emb), N.ptr(g_emb), N.ptr(mem), Q, P, N.ptr(md), N.ptr(mo)),
+                "cir_stage1_rank_members")
+        return md, mo
 
     def stage1_logits(self, q_emb: torch.Tensor, t_emb: torch.Tensor, temp: float) -> torch.Tensor:
         """q_emb [Q,256] @ t_emb [G,256]^T / temp in fp32 (src/blip_stage1.py:90-91)."""
@@ -571,7 +614,9 @@ def get_engine(device=None, precision: str = "bf16") -> Engine:
     """Process-wide engine cache (one per device and precision)."""
     if not torch.cuda.is_available():
         raise N.CirError("no CUDA device: the B200 path has no CPU fallback")
-    idx = torch.cuda.current_device() if device is None else (torch.device(device).index or torch.cuda.current_device())
+    idx = None if device is None else torch.device(device).index       # index 0 is a valid explicit choice
+    if idx is None:
+        idx = torch.cuda.current_device()
     key = (idx, precision)
     if key not in _engines:
         _engines[key] = Engine(torch.device("cuda", idx), precision)

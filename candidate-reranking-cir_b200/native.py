@@ -111,6 +111,7 @@ _SIGS = {
     "cir_stage1_topk": (C.c_int, [vp, vp, vp, i64, i64, vp, i64, i64, vp, vp, vp, C.c_size_t]),
     "cir_stage1_topk_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
     "cir_stage1_logits": (C.c_int, [vp, vp, vp, i64, i64, C.c_float, vp]),
+    "cir_stage1_rank_members": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp]),
     "cir_topk_merge": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp, vp, C.c_size_t]),
     "cir_recall_counts": (C.c_int, [vp, vp, vp, i64, i64, C.POINTER(i32), i32, vp]),
     "cir_vit_workspace_bytes": (C.c_size_t, [vp, i64, i64]),

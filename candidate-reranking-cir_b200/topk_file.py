@@ -39,7 +39,8 @@ def save_topk(path: str, d: Dict) -> None:
 
 def load_topk(path: str, K: int, split: str, dress_type: Optional[str] = None, index_names: Optional[List[str]] = None,
               target_names: Optional[List[str]] = None) -> Dict:
-    """Same sanity checks as the reference datasets (src/data_utils.py:169-171,293-303); returns
+    """Same sanity checks as the reference datasets (src/data_utils.py:169-171,293-303): ``dress_type`` given -> the
+    Fashion-IQ reader (:166-179), otherwise the CIRR reader (:290-305), which REQUIRES ``group_labels``.  Returns
     ``K_sorted_index_names`` [Q,K], ``K_labels`` numpy bool [Q,K] (None on test1), ``K_group_labels``,
     ``K_target_names``, ``K_index_names``, ``K``."""
     f = torch.load(path, weights_only=False)
@@ -53,8 +54,8 @@ def load_topk(path: str, K: int, split: str, dress_type: Optional[str] = None, i
            "K_labels": None, "K_group_labels": None, "K_target_names": f.get("target_names")}
     if split != "test1":
         out["K_labels"] = f["labels"][:, :K].numpy()                    # :174, :300
-        if "group_labels" in f:
-            out["K_group_labels"] = f["group_labels"].numpy()           # :301
+        if dress_type is None:                                          # CIRR reader: the key is read unconditionally (:301)
+            out["K_group_labels"] = f["group_labels"].numpy()
         if target_names is not None:
             assert out["K_target_names"] == list(target_names), "Something is wrong."  # :303
     return out

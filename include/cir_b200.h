@@ -202,6 +202,13 @@ size_t cir_stage1_topk_workspace_bytes(int64_t Q, int64_t G, int64_t K);
  * Replaces `predicted_features @ target_features.T / self.temp` (src/blip_stage1.py:90-91), forward only. */
 int cir_stage1_logits(cir_ctx* ctx, const float* q_emb, const float* t_emb, int64_t Q, int64_t G, float temp, float* logits);
 
+/* Stage-I ranking of P named gallery rows per query (the CIRR "img_set" group members without the reference image):
+ * member_dist[q,j] = 1 - q_emb[q] . g_emb[members[q,j]] with the arithmetic of cir_stage1_topk, member_order[q,r] = slot j of
+ * the r-th closest member (ties -> lowest gallery row).  Yields `group_labels` of the stage-I top-K file without the full
+ * [Q,G] sort: src/validate.py:213-218 (labels[group_mask]), written at :256-263 and read at src/data_utils.py:301.  P <= 32. */
+int cir_stage1_rank_members(cir_ctx* ctx, const float* q_emb, const float* g_emb, const int32_t* members, int64_t Q,
+                            int64_t P, float* member_dist, int32_t* member_order);
+
 /* Merge P per-shard sorted lists pairs[p][Q][K] -> best K per query (ascending dist, ties ->
  * lowest global index).  The NCCL all-gather that assembles `dist_in/idx_in` is done by the host. */
 int cir_topk_merge(cir_ctx* ctx, const float* dist_in, const int32_t* idx_in, int64_t P, int64_t Q,

@@ -212,6 +212,24 @@ def stage1_topk(q_emb: torch.Tensor, g_emb: torch.Tensor, exclude: Optional[torc
     return torch.gather(dist, 1, idx), idx
 
 
+def cirr_stage1_lists(q_emb: torch.Tensor, g_emb: torch.Tensor, ref_idx: Sequence[int], target_idx: Sequence[int],
+                      group_noref: Sequence[Sequence[int]]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The index bookkeeping of compute_cirr_val_metrics, src/validate.py:202-218, on gallery ROW indices instead of names:
+    full ascending ranking, reference removed (:207-210), labels (:213-214), ``group_labels = labels[group_mask]`` (:216-218).
+    -> (sorted rows [Q,G-1] int64, labels bool [Q,G-1], group_labels bool [Q,P])."""
+    dist = 1 - q_emb.float() @ g_emb.float().T
+    order = torch.sort(dist, dim=-1, stable=True).indices
+    Q, G = order.shape
+    ref = torch.as_tensor(np.asarray(ref_idx), dtype=torch.int64)
+    tgt = torch.as_tensor(np.asarray(target_idx), dtype=torch.int64)
+    noref = order[order != ref[:, None]].reshape(Q, G - 1)
+    labels = noref == tgt[:, None]
+    members = torch.as_tensor(np.asarray(group_noref), dtype=torch.int64)
+    group_mask = (noref[..., None] == members[:, None, :]).sum(-1).bool()
+    group_labels = labels[group_mask].reshape(Q, -1)
+    return noref, labels, group_labels
+
+
 # --------------------------------------------------------------------------- re-sort + recall
 
 def rerank_order(scores: torch.Tensor) -> torch.Tensor:

@@ -13,6 +13,11 @@ hot path is made of, and stores inputs + outputs as small ``.npz`` files:
       stage-I top-K, z_t, stage-II 1536-d features and scores, sorted labels, recalls.
   * ``stage2_L32.npz``      -- reference-style init, Q=1, L=32 full mask, K=3 (BASELINE shape).
   * ``training_forward.npz`` -- the in-batch B x B forward of both stages (train=True paths), B=3.
+  * ``config1_8x50.npz``     -- BASELINE.json configs[0]: 8 queries x top-50 (stage-I lists of the same run), L=32,
+      reference-style init, 384 px, G=56; targets planted at ranks with a score margin so that Recall@{1,5,10,50}
+      is well defined under the bf16 tolerance.
+  * ``interop.npz``          -- reference-function outputs for format work: ``interpolate_pos_embed`` (src/vit.py:281-305)
+      on a 224 px -> 384 px resize, and the CIRR stage-I writer lines (src/validate.py:202-226) on a small distance matrix.
 
 The few lines of ``validate.py`` / ``validate_stage2.py`` that need datasets are restated
 inline with their file:line (they are index bookkeeping around the model calls).
@@ -119,7 +124,141 @@ def run_training_forward(name, *, seed, style, G, B, L, min_len):
     print(f"{name}: {time.time() - t0:.1f}s  s2_logits={s2_logits.numpy().round(4).tolist()}")
 
 
+def run_config1(name, *, seed=2, G=56, Q=8, K=50, L=32):
+    """BASELINE.json configs[0]: 8 synthetic queries x top-50 candidates, 384 px, reference-style random init.
+    Candidate lists come from the reference's own stage I on the same inputs (CIRR mode: reference removed,
+    src/validate.py:202-210); scoring follows src/validate_stage2.py:235-258.  Labels are synthetic: for query q the
+    target is planted at a chosen rank of the REFERENCE's fp32 ranking, picking inside each recall bucket the candidate
+    with the largest score margin to the bucket edges, so Recall@{1,5,10,50} is a meaningful
+    parity check for a bf16 implementation; one query has no positive (filled row, src/validate_stage2.py:123,258)."""
+    t0 = time.time()
+    sd1 = syn.make_stage1_state_dict(seed, 384, "reference")
+    sd2 = syn.make_stage2_state_dict(seed, 384, "reference", head_gain=1.0)
+    m1, m2, tok, _ = build_models(sd1, sd2)
+    images = syn.make_images(G, 384, seed=1)
+    ref_idx, _, ids, mask = syn.make_queries(Q, G, L, seed=3, min_len=None)
+    feats_in = []
+    m2.cls_head.register_forward_hook(lambda mod, inp, out: feats_in.append(inp[0].detach().clone()))
+    with torch.no_grad():
+        tokens2 = m2.img_embed(images)
+        tokens1, g_emb = m1.img_embed(images, return_pool_and_normalized=True)
+        tok.push(ids, mask)
+        q_emb = F.normalize(m1.img_txt_fusion(tokens1[ref_idx], None, ["x"] * Q, train=False))
+        distances = 1 - q_emb @ g_emb.float().T
+        sorted_indices = torch.sort(distances, dim=-1, stable=True).indices
+        keep = sorted_indices != ref_idx[:, None]
+        cand_idx = sorted_indices[keep].reshape(Q, G - 1)[:, :K]
+        z_all, scores = [], []
+        for q in range(Q):
+            tok.push(ids[q:q + 1], mask[q:q + 1])
+            z = m1.img_txt_fusion(tokens2[ref_idx[q]][None], None, ["x"], train=False, return_raw=True)
+            z_all.append(z.last_hidden_state[0])
+            tok.push(ids[q:q + 1], mask[q:q + 1])
+            scores.append(m2.img_txt_fusion_val(z, tokens2[cand_idx[q]], ["x"]))
+        scores = torch.stack(scores)
+        feats = torch.stack(feats_in)
+        order = torch.sort(scores, dim=-1, descending=True, stable=True).indices
+    # ---- plant the targets.  Needed: one query with the target at rank 0, two in ranks [1,5), two in [5,10), two in
+    #      [10,50) and one whose target is outside the list.  For every (query, bucket) the best rank is the one with the
+    #      largest score margin to the bucket edges; buckets are then handed to queries greedily by that margin.
+    s_sorted = np.take_along_axis(scores.numpy(), order.numpy(), axis=1)
+
+    def best_rank(q, lo, hi):
+        best, best_m = lo, -1.0
+        for r in range(lo, hi):
+            up = s_sorted[q, lo - 1] - s_sorted[q, r] if lo > 0 else np.inf          # gap to the last rank of the bucket above
+            dn = s_sorted[q, r] - s_sorted[q, hi] if hi < K else np.inf             # gap to the first rank of the bucket below
+            if min(up, dn) > best_m:
+                best, best_m = r, min(up, dn)
+        return best, best_m
+    need = [(0, 1), (1, 5), (1, 5), (5, 10), (5, 10), (10, 50), (10, 50)]
+    target_idx = np.zeros(Q, np.int64)
+    margins = np.zeros(Q, np.float32)
+    bucket_lo = np.full(Q, -1, np.int32)
+    free = set(range(Q))
+    for lo, hi in sorted(need, key=lambda b: b[1] - b[0]):                            # narrow buckets choose first
+        q = max(free, key=lambda qq: best_rank(qq, lo, hi)[1])
+        r, m = best_rank(q, lo, hi)
+        target_idx[q] = int(cand_idx[q, order[q, r]])
+        margins[q], bucket_lo[q] = m, lo
+        free.discard(q)
+    for q in free:                                                                    # target outside the list
+        outside = [g for g in range(G) if g != int(ref_idx[q]) and g not in cand_idx[q].tolist()]
+        target_idx[q] = outside[0]
+        margins[q] = np.inf
+    k_labels = (cand_idx.numpy() == target_idx[:, None])
+    sc = scores.clone()
+    sc[~torch.tensor(k_labels).any(1)] = -99999.99                                   # src/validate_stage2.py:123,258
+    order_f = torch.sort(sc, dim=-1, descending=True, stable=True).indices
+    labels = np.take_along_axis(k_labels, order_f.numpy(), axis=1)
+    lab_t = torch.tensor(labels)
+    recalls = [(torch.sum(lab_t[:, :k]) / len(lab_t)).item() * 100 for k in (1, 5, 10, 50)]   # :196-199
+    np.savez_compressed(os.path.join(HERE, name), seed=seed, style="reference", head_gain=1.0, G=G, Q=Q, K=K, L=L,
+                        ref_idx=ref_idx.numpy(), target_idx=target_idx, ids=ids.numpy(), mask=mask.numpy(),
+                        cand_idx=cand_idx.numpy().astype(np.int32), k_labels=k_labels, z_t=torch.stack(z_all).numpy(),
+                        scores=scores.numpy(), feats=feats.numpy().astype(np.float16), order=order.numpy().astype(np.int32),
+                        margins=margins, bucket_lo=bucket_lo, recalls=np.array(recalls), tokens2_cls=tokens2[:, 0, :].numpy())
+    print(f"{name}: {time.time() - t0:.1f}s recalls={recalls} margins={margins.round(5).tolist()} "
+          f"score range=({float(scores.min()):.4f},{float(scores.max()):.4f}) std={float(scores.std()):.4f}")
+
+
+def run_interop(name):
+    """Outputs of two reference code fragments used by the format layer:
+    (1) ``vit.interpolate_pos_embed`` (src/vit.py:281-305) resizing a 224 px position table (197 tokens) to 384 px (577);
+    (2) the CIRR stage-I writer lines, src/validate.py:202-226, restated verbatim on a seeded [Q,G] distance matrix
+        (they need only numpy/torch): sorted names without the reference, labels, group_labels."""
+    sys.path.insert(0, os.path.join(os.environ.get("CIR_REFERENCE", "/root/reference"), "src"))
+    from ref_shim import load_reference
+    load_reference()
+    import vit as ref_vit
+
+    class _V:                                            # the two attributes interpolate_pos_embed reads
+        class patch_embed:
+            num_patches = (384 // 16) ** 2
+        pos_embed = torch.zeros(1, 577, 768)
+    g = torch.Generator().manual_seed(7)
+    pos224 = torch.randn(1, 197, 768, generator=g) * 0.02
+    pos384 = ref_vit.interpolate_pos_embed(pos224, _V)
+    # ---- (2) src/validate.py:202-226
+    Q, G = 7, 23
+    index_names = syn.index_names_for(G)
+    gq = torch.Generator().manual_seed(8)
+    predicted_features = F.normalize(torch.randn(Q, 256, generator=gq), dim=-1)
+    index_features = F.normalize(torch.randn(G, 256, generator=gq), dim=-1)
+    ref_i, tgt_i, _, _ = syn.make_queries(Q, G, 8, seed=9)
+    groups = syn.make_group_members(ref_i, tgt_i, G, seed=10)
+    reference_names = [index_names[i] for i in ref_i.tolist()]
+    target_names = [index_names[i] for i in tgt_i.tolist()]
+    group_members = [[index_names[i] for i in row[1:]] for row in groups.tolist()]       # reference removed (validate.py:300-303)
+    distances = 1 - predicted_features @ index_features.T
+    sorted_indices = torch.argsort(distances, dim=-1).cpu()
+    sorted_index_names = np.array(index_names)[sorted_indices]
+    reference_mask = torch.tensor(
+        sorted_index_names != np.repeat(np.array(reference_names), len(index_names)).reshape(len(target_names), -1))
+    sorted_index_names = sorted_index_names[reference_mask].reshape(sorted_index_names.shape[0], sorted_index_names.shape[1] - 1)
+    labels = torch.tensor(
+        sorted_index_names == np.repeat(np.array(target_names), len(index_names) - 1).reshape(len(target_names), -1))
+    group_members_a = np.array(group_members)
+    group_mask = (sorted_index_names[..., None] == group_members_a[:, None, :]).sum(-1).astype(bool)
+    group_labels = labels[group_mask].reshape(labels.shape[0], -1)
+    rec = [(torch.sum(labels[:, :k]) / len(labels)).item() * 100 for k in (1, 5, 10, 50)]
+    grec = [(torch.sum(group_labels[:, :k]) / len(group_labels)).item() * 100 for k in (1, 2, 3)]
+    np.savez_compressed(os.path.join(HERE, name), pos224=pos224.numpy(), pos384=pos384.numpy(),
+                        q_emb=predicted_features.numpy(), g_emb=index_features.numpy(), ref_idx=ref_i.numpy(), target_idx=tgt_i.numpy(),
+                        groups=groups.numpy(), sorted_index_names=sorted_index_names, labels=labels.numpy(),
+                        group_labels=group_labels.numpy(), recalls=np.array(rec), group_recalls=np.array(grec))
+    print(f"{name}: recalls={rec} group={grec}")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                                 # e.g. `make_golden.py config1 interop`
+        if "config1" in sys.argv:
+            run_config1("config1_8x50.npz")
+        if "interop" in sys.argv:
+            run_interop("interop.npz")
+        sys.exit(0)
     run("pipeline_small.npz", seed=0, style="dense", G=6, Q=3, K=4, L=12, min_len=8, head_gain=1.0)
     run("stage2_L32.npz", seed=1, style="reference", G=4, Q=1, K=3, L=32, min_len=None, head_gain=1.0)
     run_training_forward("training_forward.npz", seed=0, style="dense", G=6, B=3, L=12, min_len=8)
+    run_config1("config1_8x50.npz")
+    run_interop("interop.npz")

@@ -88,3 +88,70 @@ def test_checkpoint_ingestion(tmp_path):
     # interpolation matches the reference formula on an identity-size input
     same = Cp.interpolate_pos_embed(sd["visual_encoder.pos_embed"], 576)
     assert same is sd["visual_encoder.pos_embed"]
+
+
+def _load_golden(name):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+    return {k: z[k] for k in z.files}
+
+
+def test_interpolate_pos_embed_matches_reference_function():
+    """224 px -> 384 px position table against the output of the reference's own ``vit.interpolate_pos_embed``
+    (src/vit.py:281-305), generated by tests/golden/make_golden.py (interop.npz)."""
+    g = _load_golden("interop.npz")
+    got = cir.checkpoint.interpolate_pos_embed(torch.tensor(g["pos224"]), 576)
+    assert got.shape == (1, 577, 768)
+    assert np.abs(got.numpy() - g["pos384"]).max() <= 1e-6
+    assert np.array_equal(got[:, 0].numpy(), g["pos224"][:, 0])          # class token kept
+
+
+def test_cirr_topk_file_is_readable_by_the_reference_reader(tmp_path):
+    """The dict shape the CIRR stage-I driver writes (src/validate.py:256-263) from the fixture the reference's own writer
+    lines produced, through reader logic restated from src/data_utils.py:290-305 (``group_labels`` is read unconditionally)."""
+    from oracle import cir_oracle as O
+    T = cir.topk_file
+    g = _load_golden("interop.npz")
+    names = cir.synthetic.index_names_for(g["g_emb"].shape[0])
+    ref_idx, tgt_idx, groups = g["ref_idx"], g["target_idx"], g["groups"]
+    noref, labels, group_labels = O.cirr_stage1_lists(torch.tensor(g["q_emb"]), torch.tensor(g["g_emb"]), ref_idx, tgt_idx, groups[:, 1:])
+    # the oracle's index bookkeeping == the reference's name bookkeeping
+    assert np.array_equal(np.array(names)[noref.numpy()], g["sorted_index_names"])
+    assert np.array_equal(labels.numpy(), g["labels"]) and np.array_equal(group_labels.numpy(), g["group_labels"])
+    K = 10
+    d = T.make_topk_dict(np.array(names)[noref.numpy()], names, "val", target_names=[names[i] for i in tgt_idx],
+                         labels=labels, group_labels=group_labels, k=K)
+    p = os.path.join(tmp_path, "cirr_top_10_val.pt")
+    T.save_topk(p, d)
+    # ---- src/data_utils.py:290-305, restated
+    tmp_f = torch.load(p, weights_only=False)
+    assert K <= tmp_f["sorted_index_names"].shape[-1]
+    assert tmp_f["split"] == "val"
+    K_sorted_index_names = tmp_f["sorted_index_names"][:, :K]
+    assert tmp_f["index_names"] == names
+    K_labels = tmp_f["labels"][:, :K].numpy()
+    K_group_labels = tmp_f["group_labels"].numpy()
+    assert tmp_f["target_names"] == [names[i] for i in tgt_idx]
+    assert np.array_equal(K_sorted_index_names, g["sorted_index_names"][:, :K])
+    assert np.array_equal(K_labels, g["labels"][:, :K]) and np.array_equal(K_group_labels, g["group_labels"])
+    got = T.load_topk(p, K=K, split="val", index_names=names, target_names=[names[i] for i in tgt_idx])
+    assert np.array_equal(got["K_group_labels"], g["group_labels"])
+    # a CIRR file without group_labels is rejected exactly where the reference would fail (KeyError at :301)
+    d.pop("group_labels")
+    T.save_topk(p, d)
+    with pytest.raises(KeyError):
+        T.load_topk(p, K=K, split="val")
+
+
+def test_tokenizer_is_never_silently_synthetic(monkeypatch):
+    B = cir.blip
+    monkeypatch.delenv("CIR_SYNTHETIC_TOKENIZER", raising=False)
+    tok = B.init_tokenizer()
+    if isinstance(tok, B.MissingTokenizer):                 # no vocabulary on disk (this container, the GPU box)
+        assert tok.enc_token_id == 30523
+        with pytest.raises(B.CirTokenizerError):
+            tok(["a caption"])
+        assert isinstance(B.init_tokenizer(synthetic=True), cir.synthetic.SyntheticTokenizer)
+        monkeypatch.setenv("CIR_SYNTHETIC_TOKENIZER", "1")
+        assert isinstance(B.init_tokenizer(), cir.synthetic.SyntheticTokenizer)
+    else:
+        assert not isinstance(tok, cir.synthetic.SyntheticTokenizer)

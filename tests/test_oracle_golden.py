@@ -130,3 +130,37 @@ def test_training_shape_forward_matches_reference(small, golden_dir):
         z_ref = torch.tensor(g["z_t"])
         s2 = torch.stack([O.stage2_score(sd2, z_ref[i:i + 1], ids[i:i + 1], mask[i:i + 1], tokens2[target_idx]) for i in range(B)])
         assert np.abs(s2.numpy() - g["s2_logits"]).max() < 1e-4
+
+
+def test_config1_8x50_matches_reference(golden_dir):
+    """BASELINE.json configs[0] (8 queries x top-50, L=32, reference-style init): the oracle against the reference's scores for
+    two of the eight queries (the CPU budget of this suite), and the label / recall bookkeeping for all of them."""
+    g = _load(golden_dir, "config1_8x50.npz")
+    sd1 = syn.make_stage1_state_dict(int(g["seed"]), 384, "reference")
+    sd2 = syn.make_stage2_state_dict(int(g["seed"]), 384, "reference", head_gain=1.0)
+    images = syn.make_images(int(g["G"]), 384, seed=1)
+    ids, mask = torch.tensor(g["ids"]), torch.tensor(g["mask"])
+    with torch.no_grad():
+        tokens2 = O.vit_forward(sd2, images)
+        assert np.abs(tokens2[:, 0, :].numpy() - g["tokens2_cls"]).max() < 5e-5
+        for q in (0, 5):
+            z = O.stage1_hidden(sd1, tokens2[int(g["ref_idx"][q])][None], ids[q:q + 1], mask[q:q + 1])
+            assert np.abs(z[0].numpy() - g["z_t"][q]).max() < 1e-4
+            s = O.stage2_score(sd2, z, ids[q:q + 1], mask[q:q + 1], tokens2[torch.tensor(g["cand_idx"][q]).long()])
+            assert np.abs(s.numpy() - g["scores"][q]).max() <= 1e-4
+    sc = torch.tensor(g["scores"]).clone()
+    sc[~torch.tensor(g["k_labels"]).any(1)] = O.NEG_FILL
+    assert np.array_equal(O.rerank_order(torch.tensor(g["scores"])).numpy(), g["order"])
+    assert O.recall_at(O.sorted_labels(sc, g["k_labels"]), (1, 5, 10, 50)) == g["recalls"].tolist()
+    assert g["recalls"].tolist() == [12.5, 37.5, 62.5, 87.5]            # ranks 0 | [1,5) x2 | [5,10) x2 | [10,50) x2 | absent
+    assert float(g["margins"].min()) > 4e-3
+
+
+def test_cirr_stage1_lists_match_reference_writer(golden_dir):
+    g = _load(golden_dir, "interop.npz")
+    names = np.array(syn.index_names_for(g["g_emb"].shape[0]))
+    noref, labels, gl = O.cirr_stage1_lists(torch.tensor(g["q_emb"]), torch.tensor(g["g_emb"]), g["ref_idx"], g["target_idx"], g["groups"][:, 1:])
+    assert np.array_equal(names[noref.numpy()], g["sorted_index_names"])
+    assert np.array_equal(labels.numpy(), g["labels"]) and np.array_equal(gl.numpy(), g["group_labels"])
+    assert O.recall_at(labels, (1, 5, 10, 50)) == g["recalls"].tolist()
+    assert O.recall_at(gl, (1, 2, 3)) == g["group_recalls"].tolist()
