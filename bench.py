@@ -1,24 +1,28 @@
 """bench.py -- stage-II re-ranked triplets/s (BASELINE.json metric) on N B200s of one node.
 
-A "step" is one pass of the hot path over one batch of synthetic input: for every query of a
-Fashion-IQ-val-shaped category (Q queries x top-K=100 candidates) compute z_t (stage-I encoder on the
-reference image's tokens), score all Q*K triplets with the dual-stream stage-II encoder
-(candidate-major, K/V once per unique candidate), re-sort each row and count Recall@{10,50}.
-Gallery ViT tokens are the resident cache the reference also keeps on the device
-(src/utils.py:43-55); they are produced once, outside the timed region, by the ViT kernel path.
+A "step" is one pass of the hot path over one batch of synthetic input: for every query of a Fashion-IQ-val-shaped
+category (Q = 2,017 queries x top-K = 100 candidates, BASELINE configs[3]; `--job cirr`: Q = 4,181 x K = 50, configs[2])
+compute z_t (stage-I encoder on the reference image's tokens), score all Q*K triplets with the dual-stream stage-II
+encoder (candidate-major, K/V once per unique candidate), re-sort each row and count Recall@{10,50}.  Gallery ViT tokens
+are the resident cache the reference also keeps on the device (src/utils.py:43-55); they are produced once, outside the
+timed region, by the ViT kernel path.
 
   value : whole-job triplets/s with the step's inputs already resident in HBM
-  e2e   : the same metric through the public validate_stage2.compute_fiq_val_metrics call with HOST
-          (pinned) token ids / masks / candidate lists / labels copied H2D inside the timed region and
-          the order + scores read back D2H
-  roofline : the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event duration per launch,
-          against the measured sustained bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline : the CPU oracle (a port of the reference's PyTorch arithmetic) on the host cores, on a
-          bounded sample of the same workload
+  e2e   : the same metric through the public validate_stage2.compute_fiq_val_metrics call with HOST (pinned) token ids /
+          masks / candidate names / labels: name -> row join, H2D of ids, masks, reference rows, per-chunk triplet lists
+          and labels inside the timed region; the recall counters AND the re-ranked order [Q,K] are read back D2H
+  roofline : the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event duration per launch against the measured
+          sustained bf16 peak in MEASURED_PEAKS.json; `secondary` holds the same for the tcgen05 attention, the masked
+          self-attention and LayerNorm (HBM) kernels; `traffic` = DRAM bytes per launch from the committed ncu capture
+  cpu_baseline : the reference's CPU arithmetic on the host cores on a bounded sample of the same workload (the reference
+          itself through tests/golden/ref_shim.py where its sources are reachable, else the oracle port)
 
-N > 1 (torchrun): one process per GPU, weak scaling (every rank re-ranks its own Q x K block, gallery
-tokens replicated), ranks exchange only (score, order) rows with one NCCL all-gather per step.
-`--impl reference` times the reference's CPU implementation of the path (oracle port) instead.
+N > 1 (torchrun): STRONG scaling -- the job is fixed and split over the ranks.  z_t is computed for a block of queries per
+rank and all-gathered; the candidate-sorted triplet list is cut into N contiguous candidate ranges, so each gallery image's
+K/V projections are computed on one rank only and the per-GPU K/V reuse does not fall with N (`--partition query` splits
+by query block instead); ranks all-gather (position, score) pairs and every rank re-sorts.  After the timed region rank 0
+re-scores a sample of rows alone (single-GPU path) and the line carries the comparison (`cross_rank_check`).
+`--impl reference` times the reference's CPU implementation of the path instead (rank 0 only).
 """
 from __future__ import annotations
 
@@ -39,6 +43,7 @@ import torch
 F_REF_GF = 47.247          # algorithmic GFLOP per triplet as the reference executes them (L=32)
 METRIC = "stage2_reranked_triplets_per_s"
 UNIT = "triplets/s"
+JOBS = {"fiq": (2017, 100), "cirr": (4181, 50)}      # analysis_plot/fiq_stageII_labels_val_dress.pt / cirr_stageII_labels_val.pt row counts
 
 
 def parse():
@@ -47,21 +52,38 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--queries", type=int, default=2017)      # Fashion-IQ dress val (analysis_plot/fiq_stageII_labels_val_dress.pt)
-    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--job", default="fiq", choices=sorted(JOBS))
+    ap.add_argument("--queries", type=int, default=None)
+    ap.add_argument("--k", type=int, default=None)
     ap.add_argument("--gallery", type=int, default=2297)      # CIRR-val-sized token gallery (BASELINE configs[1])
     ap.add_argument("--length", type=int, default=32)
-    ap.add_argument("--cpu-sample-triplets", type=int, default=200)
+    ap.add_argument("--partition", default="candidate", choices=["candidate", "query"])
+    ap.add_argument("--cpu-sample-queries", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true")
+    a = ap.parse_args()
+    q, k = JOBS[a.job]
+    a.queries = a.queries or q
+    a.k = a.k or k
+    return a
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
-    return 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+        return (d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs", 6500.0),
+                "measured (MEASURED_PEAKS.json: bf16_tflops_sustained for kernels timed inside a long step, hbm_gbs)")
+    return 1400.0, 6500.0, "fallback (B200_PROFILING.md: sustained ~1.4 PFLOP/s bf16, ~6.5 TB/s HBM copy)"
+
+
+def committed_traffic():
+    """DRAM bytes per launch of this repo's kernels from the committed ncu capture (profiles/r02_dram_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -92,13 +114,14 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons}
 
 
-def synth_workload(args, rank):
+def synth_workload(args, seed=0):
+    """The job (identical on every rank): queries, stage-I-like candidate lists (K distinct gallery rows per query, never the
+    reference; the target planted in ~98 % of the lists), labels."""
     import cir_b200 as cir
     syn = cir.synthetic
     Q, K, G, L = args.queries, args.k, args.gallery, args.length
-    ref, tgt, ids, mask = syn.make_queries(Q, G, L, seed=300 + rank)
-    g = torch.Generator().manual_seed(400 + rank)
-    # stage-I-like candidate lists: K distinct gallery rows per query, never the reference; the target planted in ~98 %
+    ref, tgt, ids, mask = syn.make_queries(Q, G, L, seed=300 + seed)
+    g = torch.Generator().manual_seed(400 + seed)
     scores = torch.rand(Q, G, generator=g)
     scores[torch.arange(Q), ref] = -1.0
     hit = torch.rand(Q, generator=g) < 0.98
@@ -110,12 +133,23 @@ def synth_workload(args, rank):
     return ref.int(), tgt, ids.int(), mask.int(), cand, labels
 
 
-def run_reference(args, rank, world, emit):
-    """Reference arm: the reference's CPU arithmetic (oracle port; the Python reference itself cannot
-    travel to the box) on all host threads, each step a bounded sample of the same workload."""
-    if rank != 0:
-        return
-    from oracle import cir_oracle as O
+def workload_text(args):
+    return (f"stage2_rerank_{args.job}_shape: Q={args.queries} queries x K={args.k} candidates (whole job), L={args.length} tokens, "
+            f"G={args.gallery} gallery images (577 ViT-B/16 tokens each, resident), z_t + stage-II + re-sort + recall")
+
+
+# ----------------------------------------------------------------------------------------------- CPU arms
+def find_reference():
+    """The reference's own sources, if reachable (never on the GPU box): $CIR_REFERENCE, /root/reference, ./baseline/_ref."""
+    for p in (os.environ.get("CIR_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if p and os.path.exists(os.path.join(p, "src", "blip_stage2.py")):
+            return p
+    return None
+
+
+def cpu_scorer(args):
+    """-> (score_one_query(qi), kind, note).  The UNMODIFIED reference modules behind tests/golden/ref_shim.py when the
+    reference's sources are reachable, otherwise the CPU oracle (a restatement of the same arithmetic)."""
     import cir_b200 as cir
     syn = cir.synthetic
     cores = os.cpu_count() or 1
@@ -123,64 +157,78 @@ def run_reference(args, rank, world, emit):
     sd1 = syn.make_stage1_state_dict(0, 384, "reference")
     sd2 = syn.make_stage2_state_dict(0, 384, "reference")
     L, K = args.length, args.k
-    n_trip = max(10, min(args.cpu_sample_triplets, 50))          # per step; ~4 s at ~12 triplets/s
     g = torch.Generator().manual_seed(0)
-    tokens = torch.randn(n_trip + 1, 577, 768, generator=g)      # LayerNorm-like statistics (mean 0, std 1)
-    ids, mask = syn.make_token_ids(1, L, seed=2)
+    tokens = torch.randn(K + 1, 577, 768, generator=g)          # LayerNorm-like statistics (mean 0, std 1)
+    ids, mask = syn.make_token_ids(8, L, seed=2)
     ids[:, 0] = syn.ENC_TOKEN_ID
+    ref_path = find_reference()
+    if ref_path is not None:
+        try:
+            os.environ["CIR_REFERENCE"] = ref_path
+            sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+            from ref_shim import build_models
+            m1, m2, tok, _ = build_models(sd1, sd2)
 
-    def step():
-        with torch.no_grad():
-            z = O.stage1_hidden(sd1, tokens[:1], ids, mask)
-            s = O.stage2_score(sd2, z, ids, mask, tokens[1:])
-            O.rerank_order(s[None])
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
-    v = n_trip / dt
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"stage2_rerank_fiq_shape: Q={args.queries} queries x K={K} candidates per GPU, L={L} tokens, "
-                                   f"G={args.gallery} gallery images (577 ViT-B/16 tokens each, resident), z_t + stage-II + re-sort + recall",
-                       "sample": f"each step = 1 query x {n_trip} candidates of that workload on the host CPU"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"1 query x {n_trip} candidates per step (z_t + stage-II + sort), fp32, torch CPU {cores} threads"},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    emit(line)
-
-
-def cpu_baseline(args):
+            def one(qi):
+                q = qi % 8
+                with torch.no_grad():
+                    tok.push(ids[q:q + 1], mask[q:q + 1])
+                    z = m1.img_txt_fusion(tokens[:1], None, ["x"], train=False, return_raw=True)        # validate_stage2.py:105-106
+                    tok.push(ids[q:q + 1], mask[q:q + 1])
+                    s = m2.img_txt_fusion_val(z, tokens[1:], ["x"])                                     # :118
+                    torch.argsort(s[None], dim=-1, descending=True)                                     # :53
+            return one, "reference", f"unmodified reference modules from {ref_path} (import shims: tests/golden/ref_shim.py)", cores
+        except Exception as ex:                                  # fall through to the port
+            print(f"bench: reference at {ref_path} not usable ({type(ex).__name__}: {ex}); using the oracle port", file=sys.stderr)
     from oracle import cir_oracle as O
-    import cir_b200 as cir
-    syn = cir.synthetic
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sd1 = syn.make_stage1_state_dict(0, 384, "reference")
-    sd2 = syn.make_stage2_state_dict(0, 384, "reference")
-    L = args.length
-    per_q = 50
-    nq = max(1, args.cpu_sample_triplets // per_q)
-    g = torch.Generator().manual_seed(0)
-    tokens = torch.randn(per_q + 1, 577, 768, generator=g)
-    ids, mask = syn.make_token_ids(nq, L, seed=2)
-    ids[:, 0] = syn.ENC_TOKEN_ID
-    with torch.no_grad():                                        # warm-up
-        O.stage2_score(sd2, O.stage1_hidden(sd1, tokens[:1], ids[:1], mask[:1]), ids[:1], mask[:1], tokens[1:9])
-        t0 = time.perf_counter()
-        for q in range(nq):
+
+    def one(qi):
+        q = qi % 8
+        with torch.no_grad():
             z = O.stage1_hidden(sd1, tokens[:1], ids[q:q + 1], mask[q:q + 1])
             s = O.stage2_score(sd2, z, ids[q:q + 1], mask[q:q + 1], tokens[1:])
             O.rerank_order(s[None])
-        dt = time.perf_counter() - t0
-    return {"value": nq * per_q / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{nq} queries x {per_q} candidates (z_t + stage-II + sort per query, as src/validate_stage2.py:94-125), fp32, torch CPU {cores} threads"}
+    return one, "port", "oracle/cir_oracle.py (the reference's sources are not reachable on this box)", cores
 
 
+def run_reference(args, rank, emit):
+    """Reference arm: the reference's CPU implementation of the path on all host threads; each step = one query x K candidates
+    of the workload (z_t + img_txt_fusion_val + argsort, as src/validate_stage2.py:94-125)."""
+    if rank != 0:
+        return
+    one, kind, note, cores = cpu_scorer(args)
+    K = args.k
+    for i in range(args.warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        one(args.warmup + i)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    v = K / dt
+    sample = f"1 query x K={K} candidates per step (z_t + stage-II + sort), fp32, torch CPU {cores} threads; {note}"
+    emit({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+          "dtype": "f32", "data": "synthetic",
+          "config": {"workload": workload_text(args), "sample": f"each step = 1 query x {K} candidates of that workload on the host CPU"},
+          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "gpu_launches": 0})
+
+
+def cpu_baseline(args):
+    one, kind, note, cores = cpu_scorer(args)
+    nq = max(1, args.cpu_sample_queries)
+    one(7)                                                       # warm-up
+    t0 = time.perf_counter()
+    for q in range(nq):
+        one(q)
+    dt = time.perf_counter() - t0
+    return {"value": nq * args.k / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{nq} queries x K={args.k} candidates (z_t + stage-II + sort per query, as src/validate_stage2.py:94-125), fp32, "
+                      f"torch CPU {cores} threads; {note}"}
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
 def main():
     # stdout carries exactly ONE JSON line: everything else a library prints there (e.g. "NCCL version ..." on the
     # first collective) is routed to stderr by pointing fd 1 at fd 2 until the line is ready
@@ -198,10 +246,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world, emit)
+        run_reference(args, rank, emit)
         return
     import cir_b200 as cir
     import torch.distributed as dist
+    N = cir.native
+    D = cir.distributed
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -209,7 +259,7 @@ def main():
     syn = cir.synthetic
     Q, K, G, L = args.queries, args.k, args.gallery, args.length
 
-    # ---- models (random-init, reference init style) and the resident gallery token cache
+    # ---- models (random-init, reference init style) and the resident gallery token cache (replicated: 2 GB of 180)
     sd1 = syn.make_stage1_state_dict(0, 384, "reference")
     sd2 = syn.make_stage2_state_dict(0, 384, "reference")
     m1 = cir.blip_stage1.blip_stage1(image_size=384, state_dict=sd1, precision="bf16", device=dev)
@@ -223,7 +273,7 @@ def main():
         tokens[g0:g0 + n] = m2.img_embed(torch.randn(n, 3, 384, 384, generator=gi))
     torch.cuda.synchronize()
 
-    ref, tgt, ids, mask, cand, labels = synth_workload(args, rank)
+    ref, tgt, ids, mask, cand, labels = synth_workload(args)
     names = syn.index_names_for(G)
     ref_d, ids_d, mask_d = ref.to(dev), ids.to(dev), mask.to(dev)
     cand_np = cand.numpy()
@@ -232,36 +282,28 @@ def main():
     n_trip = int(row_active.sum()) * K                            # rows without a positive are filled, not scored (:95,:123)
 
     def step_resident():
-        z_t, _ = m1.encode_queries(tokens, ref_d, ids_d, mask_d, want_z=True, want_emb=False)
-        scores = m2.score_triplets(z_t, ids_d, mask_d, tokens, cand_np, row_active)
+        if args.partition == "candidate":
+            z_all = D.encode_queries_sharded(m1, tokens, ref_d, ids_d, mask_d)
+            scores = D.score_matrix_sharded(m2, tokens, z_all, ids_d, mask_d, cand_np, row_active)
+        else:
+            scores = D.stage2_scores_gpu(m1, m2, tokens, ref_d, ids_d, mask_d, cand_np, row_active, mode="query")
         order = eng.rerank_sort(scores)
-        hits = eng.recall_counts(labels_d, order, (10, 50))
-        if world > 1:
-            out = [torch.empty_like(scores) for _ in range(world)]
-            dist.all_gather(out, scores)
-            outo = [torch.empty_like(order) for _ in range(world)]
-            dist.all_gather(outo, order)
+        hits = eng.recall_counts(labels_d, order, (10, 50), sync=False)     # stays on the device: the host plans the next step meanwhile
         return scores, order, hits
 
     # host-resident inputs for the e2e leg (pinned)
     tb = syn.TokenBatch(input_ids=ids.long().pin_memory(), attention_mask=mask.long().pin_memory())
     ds = syn.SyntheticRelativeDataset(names, ref, tgt, ["x"] * Q, cand_np, kind="fiq", token_batch=tb)
-
     V2 = cir.validate_stage2
 
     def step_e2e():
-        # the reference's own entry point for this path (src/validate_stage2.py:33-66) on a dataset object whose
-        # token ids / masks / candidate names / labels live in HOST memory: every step re-tokenises from the host
-        # batch, maps names to gallery rows, uploads ids, masks, per-chunk triplet lists and labels (H2D), scores,
-        # re-sorts, and reads the recall counters back (D2H)
-        r10, r50 = V2.compute_fiq_val_metrics(ds, m2, m1, tokens, names)
-        torch.cuda.synchronize()
-        return r10, r50
-    # bytes per step, counted from the tensors the call copies: int64 ids+mask, int32 reference rows, bool labels,
-    # per triplet flat position (8) + query row (4) + candidate slot (4), per-chunk candidate/query lists and
-    # attention work lists (16 B per 8 query tiles + 16 B per 128-row tile + 16 B per 128 CLS rows)
-    h2d = 2 * Q * L * 8 + Q * 4 + Q * K + n_trip * 16 + n_trip * (16 // 4 + 16 // 4 + 1) + 2 * (Q + G) * 4
-    d2h = 2 * 8
+        # the reference's own entry point for this path (src/validate_stage2.py:33-66) on a dataset object whose token ids /
+        # masks / candidate names / labels live in HOST memory: every step joins names to gallery rows, uploads ids, masks,
+        # reference rows, the per-chunk triplet lists and the labels (H2D), scores, re-sorts, and reads the recall counters
+        # and the re-ranked order back (D2H).  Under torchrun the same call shards itself over the ranks.
+        r10, r50, order = V2.compute_fiq_val_metrics(ds, m2, m1, tokens, names, return_order=True)
+        return r10, r50, order
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -271,8 +313,9 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        out = None
         for _ in range(steps):
-            fn()
+            out = fn()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -280,7 +323,7 @@ def main():
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms / steps
+        return ms / steps, out
 
     for _ in range(args.warmup):
         step_resident()
@@ -288,17 +331,54 @@ def main():
     sampler.start()
     eng.launch_count(reset=True)
     eng.profile_gemm(True)
-    ms_step = timed(step_resident, args.steps)
+    ms_step, (scores_last, order_last, hits_last) = timed(step_resident, args.steps)
     eng.profile_gemm(False)
-    launches = eng.launch_count() + m1.engine.launch_count() * 0   # same engine object for both models
-    gemm_ms, gemm_flops, gemm_n = eng.profile_gemm_read()
+    launches = eng.launch_count()
+    prof = {k: eng.profile_read(k) for k in (N.PROF_GEMM, N.PROF_ATTN_TC, N.PROF_ATTN_SELF, N.PROF_LAYERNORM, N.PROF_QKV_ATTN)}
+    gemm_ms, gemm_flops, gemm_n = prof[N.PROF_GEMM]
+    plan = dict(eng.last_plan)
     step_e2e()
-    ms_e2e = timed(step_e2e, max(1, args.steps))
+    eng.h2d_bytes = 0
+    ms_e2e, (r10, r50, order_host) = timed(step_e2e, max(1, args.steps))
+    # bytes per step counted from the tensors the call copies: engine uploads (per-chunk lists, counted by the engine) +
+    # int64 ids/mask (tokenize) + bool labels; D2H: the order [Q,K] int32 and two int64 counters
+    h2d = eng.h2d_bytes // max(1, args.steps) + 2 * Q * L * 8 + 2 * Q * L * 4 + Q * 4 + Q * K
+    d2h = Q * K * 4 + 2 * 8
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # ---- secondary figures of the same path (outside the timed region): stage-I candidate filtering
-    #      (BASELINE configs[1]: cosine + top-100 over the 2.3k gallery, Q = 4,181) and ViT token extraction
+    # ---- N-GPU == 1-GPU: rank 0 re-scores a sample of rows alone, through the single-process path (no partition, no
+    #      collectives), and compares with the rows the sharded step produced
+    check = None
+    if world > 1:
+        if rank == 0:
+            rows = np.flatnonzero(row_active)[:: max(1, int(row_active.sum()) // 48)][:48]
+            r_t = torch.from_numpy(rows).to(dev)
+            z1, _ = m1.encode_queries(tokens, ref_d[r_t], ids_d[r_t], mask_d[r_t], want_z=True, want_emb=False)
+            pos, sc = eng.stage2_score_pairs(m2._w, tokens, z1, ids_d[r_t], mask_d[r_t], cand_np[rows], None, part=None)
+            alone = torch.empty(len(rows) * K, dtype=torch.float32, device=dev)
+            alone.index_copy_(0, pos, sc)
+            alone = alone.view(len(rows), K)
+            diff = (alone - scores_last[r_t]).abs().max().item()
+            same_order = bool(torch.equal(eng.rerank_sort(alone), order_last[r_t]))
+            check = {"rows": int(len(rows)), "triplets": int(len(rows) * K), "bit_equal": bool(torch.equal(alone, scores_last[r_t])),
+                     "max_abs_diff": diff, "order_equal": same_order}
+            assert diff <= 1e-6, f"N-GPU scores differ from the single-GPU path by {diff}"
+        barrier()
+
+    # ---- weak-scaling figure for comparison with round 1 (every rank re-ranks the WHOLE job by itself, no collectives)
+    extras = {}
+    if world > 1 and not args.no_extras:
+        def step_alone():
+            z, _ = m1.encode_queries(tokens, ref_d, ids_d, mask_d, want_z=True, want_emb=False)
+            s = m2.score_triplets(z, ids_d, mask_d, tokens, cand_np, row_active)
+            return eng.rerank_sort(s)
+        step_alone()
+        ms_weak, _ = timed(step_alone, 2)
+        extras["weak_scaling"] = {"value": world * n_trip / (ms_weak / 1e3), "unit": UNIT, "ms_per_step": ms_weak,
+                                  "note": "every rank re-ranks the whole job independently (round-1 definition), 2 steps"}
+
+    # ---- secondary figures of the same path (outside the timed region, rank 0)
     def _time(fn, it=3):
         fn(); torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -307,22 +387,40 @@ def main():
             fn()
         b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b) / it
-    extras = {}
-    if rank == 0:
+    if rank == 0 and not args.no_extras:
         gq = torch.Generator().manual_seed(5)
         qe = torch.nn.functional.normalize(torch.randn(4181, 256, generator=gq), dim=-1).to(dev)
         ge = m1.engine.stage1_gallery_embed(m1._w, tokens)
         ex = torch.randint(0, G, (4181,), generator=gq)
         ms1 = _time(lambda: eng.stage1_topk(qe, ge, 100, exclude=ex))
+        extras["stage1_topk"] = {"queries_per_s": 4181 / (ms1 / 1e3), "Q": 4181, "G": G, "K": 100, "ms": ms1,
+                                 "note": "BASELINE configs[1]: fused 1 - q @ G^T + per-query top-100 with the reference index excluded"}
+        try:                                                     # 1 M-image gallery (BASELINE configs[4], one GPU's view)
+            big = torch.nn.functional.normalize(torch.randn(1_000_000, 256, generator=gq), dim=-1).to(dev)
+            ms1m = _time(lambda: eng.stage1_topk(qe, big, 200, exclude=None), it=2)
+            extras["stage1_topk_1M"] = {"queries_per_s": 4181 / (ms1m / 1e3), "Q": 4181, "G": 1_000_000, "K": 200, "ms": ms1m,
+                                        "algorithmic_tflops": 2 * 256 * 4181 * 1e6 / (ms1m / 1e3) / 1e12}
+            del big
+        except Exception as ex_:                                 # never let a secondary leg break the bench line
+            extras["stage1_topk_1M"] = {"error": repr(ex_)[:200]}
         img = torch.randn(64, 3, 384, 384, device=dev)
         msv = _time(lambda: eng.vit_forward(m2._vit, img, batch=64), it=2)
-        extras = {"stage1_topk": {"queries_per_s": 4181 / (ms1 / 1e3), "Q": 4181, "G": G, "K": 100, "ms": ms1,
-                                  "note": "fused fp32 1 - q @ G^T + per-query top-100 with the reference index excluded"},
-                  "vit_b16_384": {"images_per_s": 64 / (msv / 1e3), "batch": 64, "ms": msv}}
-
-        # the reference's per-query formulation on stock PyTorch (ATen / cuBLAS) on this same B200: the oracle's torch
-        # code with weights and inputs moved to the GPU -- the library baseline SURVEY 8(d) asks for, since the
-        # reference ships no Blackwell kernel.  Bounded sample: 4 queries x K candidates, fp32 and bf16 autocast.
+        extras["vit_b16_384"] = {"images_per_s": 64 / (msv / 1e3), "batch": 64, "ms": msv}
+        # K/V reuse = 1: every triplet names a different gallery image (what a 1 M-image gallery with disjoint lists looks like)
+        try:
+            q1 = min(22, Q)
+            perm = torch.randperm(G, generator=gq)[: q1 * min(K, G // q1)].view(q1, -1).int().numpy()
+            z1, _ = m1.encode_queries(tokens, ref_d[:q1], ids_d[:q1], mask_d[:q1], want_z=True, want_emb=False)
+            old = eng.max_candidates
+            eng.max_candidates = 512
+            ms_r1 = _time(lambda: m2.score_triplets(z1, ids_d[:q1], mask_d[:q1], tokens, perm), it=2)
+            eng.max_candidates = old
+            extras["reuse_1"] = {"triplets_per_s": perm.size / (ms_r1 / 1e3), "triplets": int(perm.size), "ms": ms_r1,
+                                 "note": "no K/V reuse: every triplet projects its own candidate's K/V (32.7 GF extra per triplet); chunk = 512 candidates"}
+        except Exception as ex_:
+            extras["reuse_1"] = {"error": repr(ex_)[:200]}
+        # the reference's per-query formulation on stock PyTorch (ATen / cuBLAS) on this same B200: the oracle's torch code
+        # with weights and inputs moved to the GPU -- the library baseline SURVEY 8(d) asks for
         try:
             from oracle import cir_oracle as O
             sd1c = {k: v.to(dev) for k, v in syn.make_stage1_state_dict(0, 384, "reference").items()}
@@ -343,39 +441,60 @@ def main():
                                             "sample": f"4 queries x {K} candidates, per-query loop as in src/validate_stage2.py:94-125 (z_t + "
                                                       "img_txt_fusion_val + argsort), oracle torch code on cuda"}
             del sd1c, sd2c, tok32
-        except Exception as ex:                                  # never let a baseline leg break the bench line
-            extras["stock_pytorch_b200"] = {"error": repr(ex)[:200]}
+        except Exception as ex_:
+            extras["stock_pytorch_b200"] = {"error": repr(ex_)[:200]}
 
-    total_trip = n_trip
-    if world > 1:
-        t = torch.tensor([float(n_trip)], device=dev)
-        dist.all_reduce(t)
-        total_trip = float(t.item())
-    value = total_trip / (ms_step / 1e3)
-    e2e_value = total_trip / (ms_e2e / 1e3)
-    peak, how = measured_peaks()
+    value = n_trip / (ms_step / 1e3)
+    e2e_value = n_trip / (ms_e2e / 1e3)
+    peak, hbm_peak, how = measured_peaks()
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_baseline(args)
+        traffic = committed_traffic()
+        step_ms_total = ms_step * args.steps
+
+        def sec(kind, name, unit, pk, bound):
+            ms, wk, n = prof[kind]
+            if n == 0:
+                return None
+            a = wk / (ms / 1e3) / (1e12 if unit == "TFLOP/s" else 1e9)
+            return {"kernel": name, "bound": bound, "achieved": a, "peak": pk, "unit": unit, "frac": a / pk if pk else None,
+                    "launches": int(n), "avg_launch_ms": ms / n, "share_of_step": ms / step_ms_total,
+                    "traffic": (traffic.get(name) or {}).get("dram_bytes_per_launch")}
+        secondary = [x for x in (
+            sec(N.PROF_ATTN_TC, "fatc::attention_tc_kernel", "TFLOP/s", peak, "tensor (MUFU.EX2 co-limited: see DESIGN.md 5)"),
+            sec(N.PROF_QKV_ATTN, "qkvattn::qkv_attention_kernel", "TFLOP/s", peak, "tensor"),
+            sec(N.PROF_ATTN_SELF, "attention_small_kernel", "TFLOP/s", peak, "hbm (QKV re-read)"),
+            sec(N.PROF_LAYERNORM, "add_layernorm_kernel", "GB/s", hbm_peak, "hbm")) if x]
+        exec_flops = gemm_flops + prof[N.PROF_ATTN_TC][1] + prof[N.PROF_ATTN_SELF][1] + prof[N.PROF_QKV_ATTN][1]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"stage2_rerank_fiq_shape: Q={Q} queries x K={K} candidates per GPU, L={L} tokens, "
-                                   f"G={G} gallery images (577 ViT-B/16 tokens each, resident), z_t + stage-II + re-sort + recall",
-                       "triplets_scored_per_gpu_step": n_trip, "chunk_triplets": eng.max_triplets, "chunk_candidates": eng.max_candidates,
+            "config": {"workload": workload_text(args),
+                       "triplets_scored_per_step": n_trip, "chunk_triplets": eng.max_triplets, "chunk_candidates": eng.max_candidates,
                        "l2_note": "per-step working set (gallery tokens 2.0 GB + activations) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": f"dp{world} (queries sharded, weights+gallery replicated, NCCL all-gather of scores/order)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+                       "parallelism": (f"{world} ranks, {args.partition}-range partition of the fixed job; weights+gallery replicated; "
+                                       "NCCL all-gather of z_t blocks and of (position, score) pairs") if world > 1 else "single GPU",
+                       "rank0_plan": plan,
+                       "kv_reuse_triplets_per_candidate_load": plan["triplets"] / max(1, plan["candidate_loads"])},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
+                    "recall_at_10_50": [r10, r50]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "tc::gemm_tcgen05_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "peak_source": how, "traffic": None,
+                         "frac": achieved / peak if peak else None, "peak_source": how,
+                         "traffic": (traffic.get("tc::gemm_tcgen05_kernel") or {}).get("dram_bytes_per_launch"),
+                         "traffic_source": traffic.get("source"),
                          "launches": int(gemm_n), "gflop_per_launch": gemm_flops / max(1, gemm_n) / 1e9,
-                         "avg_launch_ms": gemm_ms / max(1, gemm_n), "gemm_share_of_step": gemm_ms / (ms_step * args.steps),
+                         "avg_launch_ms": gemm_ms / max(1, gemm_n), "gemm_share_of_step": gemm_ms / step_ms_total,
+                         "executed_tflops_gemm_plus_attention": exec_flops / (step_ms_total / 1e3) / 1e12,
+                         "executed_frac_of_peak": exec_flops / (step_ms_total / 1e3) / 1e12 / peak if peak else None,
                          "effective_tflops_at_F_ref": value / world * F_REF_GF / 1e3,
-                         "effective_frac_of_peak": value / world * F_REF_GF / 1e3 / peak if peak else None},
+                         "effective_frac_of_peak": value / world * F_REF_GF / 1e3 / peak if peak else None,
+                         "secondary": secondary},
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
+            "cross_rank_check": check,
             "extras": extras,
         }
         emit(line)

@@ -456,7 +456,9 @@ extern "C" int cir_attention(cir_ctx* ctx, const cir_attn_args* a) {
     const int mt = (a->Lq + 15) / 16;
     if (!a->work && a->Lq <= 32 && a->Lk <= 32 && a->Lq > 1 && ctx->attn_impl == 0) {      // masked text self-attention
       const int64_t warps = (int64_t)a->B * a->H;
+      cir_prof_begin(ctx, CIR_PROF_ATTN_SELF, 4.0 * (double)a->B * a->H * (double)a->Lq * (double)a->Lk * 64.0);
       attention_small_kernel<<<(unsigned)((warps + SM_WARPS - 1) / SM_WARPS), SM_WARPS * 32, 0, ctx->stream>>>(*a);
+      cir_prof_end(ctx);
       CIR_LAUNCH_CHECK(ctx);
       return CIR_OK;
     }

@@ -448,7 +448,9 @@ int cir_attention_tc(cir_ctx* ctx, const cir_attn_args* a) {
   if (total == 0) return CIR_OK;
   if (total >= (1ll << 31)) return CIR_EUNSUPPORTED;
   const unsigned gx = (unsigned)std::min<int64_t>(total, (int64_t)ctx->num_sms);      // persistent: one CTA per SM
+  cir_prof_begin(ctx, CIR_PROF_ATTN_TC, 4.0 * (double)a->B * a->H * (double)a->Lq * (double)a->Lk * 64.0);
   fatc::attention_tc_kernel<<<gx, fatc::THREADS, fatc::SMEM_BYTES, ctx->stream>>>(mq, mk, mv, mo, *a, cpb, (int)ntiles, RB, (int)total);
+  cir_prof_end(ctx);
   CIR_LAUNCH_CHECK(ctx);
   return CIR_OK;
 }

@@ -35,6 +35,8 @@ struct cir_ctx {
 };
 void cir_prof_gemm_begin(cir_ctx* ctx, double flops);
 void cir_prof_gemm_end(cir_ctx* ctx);
+void cir_prof_begin(cir_ctx* ctx, int kind, double work);     // kind: CIR_PROF_*; work: algorithmic FLOPs or bytes of the launch
+void cir_prof_end(cir_ctx* ctx);
 
 void cir_set_error(const char* fmt, ...);
 

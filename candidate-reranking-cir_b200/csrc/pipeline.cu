@@ -15,27 +15,32 @@ int cir_head_dot(cir_ctx* ctx, const float* hidden, const float* w, const float*
 #include <vector>
 struct ProfState {
   std::vector<cudaEvent_t> ev;      // pairs: [2i] start, [2i+1] end
-  std::vector<double> flops;
+  std::vector<double> work;         // algorithmic FLOPs (GEMM, attention) or bytes (LayerNorm) of launch i
+  std::vector<int> kind;            // CIR_PROF_*
   size_t used = 0;                  // pairs in use
 };
-void cir_prof_gemm_begin(cir_ctx* ctx, double flops) {
+void cir_prof_begin(cir_ctx* ctx, int kind, double work) {
   if (!ctx->profiling) return;
   ProfState* ps = (ProfState*)ctx->prof;
   if (ps->used * 2 + 2 > ps->ev.size()) {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     ps->ev.push_back(a); ps->ev.push_back(b);
-    ps->flops.push_back(0.0);
+    ps->work.push_back(0.0);
+    ps->kind.push_back(0);
   }
-  ps->flops[ps->used] = flops;
+  ps->work[ps->used] = work;
+  ps->kind[ps->used] = kind;
   cudaEventRecord(ps->ev[ps->used * 2], ctx->stream);
 }
-void cir_prof_gemm_end(cir_ctx* ctx) {
+void cir_prof_end(cir_ctx* ctx) {
   if (!ctx->profiling) return;
   ProfState* ps = (ProfState*)ctx->prof;
   cudaEventRecord(ps->ev[ps->used * 2 + 1], ctx->stream);
   ps->used++;
 }
+void cir_prof_gemm_begin(cir_ctx* ctx, double flops) { cir_prof_begin(ctx, CIR_PROF_GEMM, flops); }
+void cir_prof_gemm_end(cir_ctx* ctx) { cir_prof_end(ctx); }
 
 static thread_local char g_err[1024] = "";
 void cir_set_error(const char* fmt, ...) {
@@ -98,18 +103,24 @@ extern "C" int cir_profile_gemm(cir_ctx* ctx, int enable) {
   if (enable) ps->used = 0;
   return CIR_OK;
 }
-extern "C" int cir_profile_gemm_read(cir_ctx* ctx, double* total_ms, double* total_flops, int64_t* launches) {
+extern "C" int cir_profile_read(cir_ctx* ctx, int kind, double* total_ms, double* total_work, int64_t* launches) {
   CIR_ENTER(ctx);
+  CIR_CHECK_ARG(kind >= 0 && kind < CIR_PROF_KINDS && total_ms && total_work && launches, "profile_read: bad argument");
   ProfState* ps = (ProfState*)ctx->prof;
-  double ms = 0.0, fl = 0.0;
+  double ms = 0.0, wk = 0.0;
+  int64_t n = 0;
   for (size_t i = 0; i < ps->used; i++) {
+    if (ps->kind[i] != kind) continue;
     float t = 0.f;
     CIR_CUDA(cudaEventSynchronize(ps->ev[2 * i + 1]));
     CIR_CUDA(cudaEventElapsedTime(&t, ps->ev[2 * i], ps->ev[2 * i + 1]));
-    ms += t; fl += ps->flops[i];
+    ms += t; wk += ps->work[i]; n++;
   }
-  *total_ms = ms; *total_flops = fl; *launches = (int64_t)ps->used;
+  *total_ms = ms; *total_work = wk; *launches = n;
   return CIR_OK;
+}
+extern "C" int cir_profile_gemm_read(cir_ctx* ctx, double* total_ms, double* total_flops, int64_t* launches) {
+  return cir_profile_read(ctx, CIR_PROF_GEMM, total_ms, total_flops, launches);
 }
 extern "C" int cir_set_stream(cir_ctx* ctx, void* s) { ctx->stream = (cudaStream_t)s; return CIR_OK; }
 extern "C" int cir_set_gemm_impl(cir_ctx* ctx, int impl) {

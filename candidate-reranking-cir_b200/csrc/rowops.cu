@@ -1,44 +1,55 @@
 // Bandwidth-bound row kernels: LayerNorm (+residual, twin gains), embeddings, gathers, casts,
-// L2-normalise, ViT patchify/assemble, score-head dot.  One warp per 768-wide row, 16-byte
-// vector accesses, fp32 statistics.
+// L2-normalise, ViT patchify/assemble, score-head dot.  One warp per 768-wide row, lane-interleaved
+// 16-byte vector accesses (a warp instruction covers 512 contiguous bytes), fp32 statistics.
 #include "common.cuh"
 
 namespace {
 
 constexpr int D = CIR_HIDDEN;          // 768
-constexpr int PER_LANE = D / 32;       // 24 contiguous elements per lane
+constexpr int PER_LANE = D / 32;       // 24 elements per lane (three lane-interleaved groups of 8)
 constexpr int WARPS = 8;
 
-template <typename T> __device__ __forceinline__ void load24(const T* p, float (&v)[PER_LANE]);
-template <> __device__ __forceinline__ void load24<float>(const float* p, float (&v)[PER_LANE]) {
+// Lane-interleaved row mapping: lane l owns the three 8-element groups g = l, l + 32, l + 64 of a 768-wide row (columns 8g..8g+7),
+// v[8i + j] <-> column 8 (l + 32 i) + j.  A warp-wide 16 B bf16 access then covers 512 contiguous bytes (every 32 B sector fully
+// used by one instruction); fp32 rows take two 16 B accesses per group (32 contiguous bytes per lane).
+template <typename T> __device__ __forceinline__ void load_row(const T* row, int lane, float (&v)[PER_LANE]);
+template <> __device__ __forceinline__ void load_row<float>(const float* row, int lane, float (&v)[PER_LANE]) {
 #pragma unroll
-  for (int i = 0; i < PER_LANE; i += 4) {
-    float4 t = *reinterpret_cast<const float4*>(p + i);
-    v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+  for (int i = 0; i < 3; i++) {
+    const float4* p = reinterpret_cast<const float4*>(row + (lane + 32 * i) * 8);
+    const float4 a = p[0], b = p[1];
+    v[8 * i] = a.x; v[8 * i + 1] = a.y; v[8 * i + 2] = a.z; v[8 * i + 3] = a.w;
+    v[8 * i + 4] = b.x; v[8 * i + 5] = b.y; v[8 * i + 6] = b.z; v[8 * i + 7] = b.w;
   }
 }
-template <> __device__ __forceinline__ void load24<bf16>(const bf16* p, float (&v)[PER_LANE]) {
+template <> __device__ __forceinline__ void load_row<bf16>(const bf16* row, int lane, float (&v)[PER_LANE]) {
+  uint4 t[3];
 #pragma unroll
-  for (int i = 0; i < PER_LANE; i += 8) {
-    uint4 t = *reinterpret_cast<const uint4*>(p + i);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+  for (int i = 0; i < 3; i++) t[i] = *reinterpret_cast<const uint4*>(row + (lane + 32 * i) * 8);
 #pragma unroll
-    for (int q = 0; q < 4; q++) { float2 f = __bfloat1622float2(h[q]); v[i + 2 * q] = f.x; v[i + 2 * q + 1] = f.y; }
+  for (int i = 0; i < 3; i++) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t[i]);
+#pragma unroll
+    for (int q = 0; q < 4; q++) { float2 f = __bfloat1622float2(h[q]); v[8 * i + 2 * q] = f.x; v[8 * i + 2 * q + 1] = f.y; }
   }
 }
-template <typename T> __device__ __forceinline__ void store24(T* p, const float (&v)[PER_LANE]);
-template <> __device__ __forceinline__ void store24<float>(float* p, const float (&v)[PER_LANE]) {
+template <typename T> __device__ __forceinline__ void store_row(T* row, int lane, const float (&v)[PER_LANE]);
+template <> __device__ __forceinline__ void store_row<float>(float* row, int lane, const float (&v)[PER_LANE]) {
 #pragma unroll
-  for (int i = 0; i < PER_LANE; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  for (int i = 0; i < 3; i++) {
+    float4* p = reinterpret_cast<float4*>(row + (lane + 32 * i) * 8);
+    p[0] = make_float4(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3]);
+    p[1] = make_float4(v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
+  }
 }
-template <> __device__ __forceinline__ void store24<bf16>(bf16* p, const float (&v)[PER_LANE]) {
+template <> __device__ __forceinline__ void store_row<bf16>(bf16* row, int lane, const float (&v)[PER_LANE]) {
 #pragma unroll
-  for (int i = 0; i < PER_LANE; i += 8) {
+  for (int i = 0; i < 3; i++) {
     uint4 t;
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
 #pragma unroll
-    for (int q = 0; q < 4; q++) h[q] = __floats2bfloat162_rn(v[i + 2 * q], v[i + 2 * q + 1]);
-    *reinterpret_cast<uint4*>(p + i) = t;
+    for (int q = 0; q < 4; q++) h[q] = __floats2bfloat162_rn(v[8 * i + 2 * q], v[8 * i + 2 * q + 1]);
+    *reinterpret_cast<uint4*>(row + (lane + 32 * i) * 8) = t;
   }
 }
 
@@ -52,8 +63,8 @@ __device__ __forceinline__ void layernorm24(float (&v)[PER_LANE], const float* g
   for (int i = 0; i < PER_LANE; i++) { float d = v[i] - mean; q = fmaf(d, d, q); }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
   float g[PER_LANE], b[PER_LANE];
-  load24<float>(gamma + lane * PER_LANE, g);
-  load24<float>(beta + lane * PER_LANE, b);
+  load_row<float>(gamma, lane, g);
+  load_row<float>(beta, lane, b);
 #pragma unroll
   for (int i = 0; i < PER_LANE; i++) v[i] = fmaf((v[i] - mean) * rstd, g[i], b[i]);
 }
@@ -66,16 +77,16 @@ add_layernorm_kernel(const TX* __restrict__ x, int64_t x_rows, const TR* __restr
   const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (r >= rows) return;
   float v[PER_LANE];
-  load24<TX>(x + (r % x_rows) * D + lane * PER_LANE, v);
+  load_row<TX>(x + (r % x_rows) * D, lane, v);
   if (res) {
     float t[PER_LANE];
-    load24<TR>(res + r * D + lane * PER_LANE, t);
+    load_row<TR>(res + r * D, lane, t);
 #pragma unroll
     for (int i = 0; i < PER_LANE; i++) v[i] += t[i];
   }
   const int64_t g = r / rows_per_group;
   layernorm24(v, gamma + g * D, beta + g * D, eps, lane);
-  store24<TY>(y + r * D + lane * PER_LANE, v);
+  store_row<TY>(y + r * D, lane, v);
 }
 
 // y[r] = LN2( m[r % m_rows] + LN1(raw[r]) ): LN1's statistics come as partial (sum, sum of squares) pairs written by the
@@ -88,19 +99,19 @@ ln_cross_virtual_kernel(const bf16* __restrict__ raw, const float2* __restrict__
   const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (r >= rows) return;
   float v[PER_LANE], t[PER_LANE], g[PER_LANE], b[PER_LANE];
-  load24<bf16>(raw + r * D + lane * PER_LANE, v);
-  load24<bf16>(m + (r % m_rows) * D + lane * PER_LANE, t);
+  load_row<bf16>(raw + r * D, lane, v);
+  load_row<bf16>(m + (r % m_rows) * D, lane, t);
   float s1 = 0.f, s2 = 0.f;
   for (int i = 0; i < parts; i++) { const float2 q = __ldg(stats + r * parts + i); s1 += q.x; s2 += q.y; }
   const float mu = s1 * (1.0f / D);
   const float rstd = rsqrtf(fmaxf(s2 * (1.0f / D) - mu * mu, 0.f) + eps);
   const int64_t grp = r / rows_per_group;
-  load24<float>(g1 + grp * D + lane * PER_LANE, g);
-  load24<float>(b1 + grp * D + lane * PER_LANE, b);
+  load_row<float>(g1 + grp * D, lane, g);
+  load_row<float>(b1 + grp * D, lane, b);
 #pragma unroll
   for (int i = 0; i < PER_LANE; i++) v[i] = fmaf((v[i] - mu) * rstd, g[i], b[i]) + t[i];
   layernorm24(v, g2 + grp * D, b2 + grp * D, eps, lane);
-  store24<bf16>(y + r * D + lane * PER_LANE, v);
+  store_row<bf16>(y + r * D, lane, v);
 }
 
 template <typename T>
@@ -113,12 +124,12 @@ bert_embeddings_kernel(const int32_t* __restrict__ ids, int64_t rows, int64_t L,
   if (r >= rows) return;
   const int64_t l = r % L;
   float v[PER_LANE], t[PER_LANE];
-  load24<float>(word + (int64_t)ids[r] * D + lane * PER_LANE, v);
-  load24<float>(pos + l * D + lane * PER_LANE, t);
+  load_row<float>(word + (int64_t)ids[r] * D, lane, v);
+  load_row<float>(pos + l * D, lane, t);
 #pragma unroll
   for (int i = 0; i < PER_LANE; i++) v[i] += t[i];
   layernorm24(v, gamma, beta, 1e-12f, lane);
-  store24<T>(out + r * D + lane * PER_LANE, v);
+  store_row<T>(out + r * D, lane, v);
 }
 
 // rows of `vecs` 16-byte vectors; grid-stride over (row, vec)
@@ -202,8 +213,8 @@ head_dot_kernel(const float* __restrict__ hidden, const float* __restrict__ w, c
   const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (r >= rows) return;
   float hv[PER_LANE], wv[PER_LANE];
-  load24<float>(hidden + r * D + lane * PER_LANE, hv);
-  load24<float>(w + lane * PER_LANE, wv);
+  load_row<float>(hidden + r * D, lane, hv);
+  load_row<float>(w, lane, wv);
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < PER_LANE; i++) s = fmaf(hv[i], wv[i], s);
@@ -227,6 +238,10 @@ extern "C" int cir_add_layernorm(cir_ctx* ctx, const void* x, int x_f32, int64_t
   CIR_CHECK_ARG(x && gamma && beta && y && x_rows > 0 && rows_per_group > 0, "add_layernorm: null/zero argument");
   const bool f32 = ctx->dtype == CIR_DTYPE_F32;
   dim3 grid(row_blocks(rows)), block(WARPS * 32);
+  {
+    const double es = f32 ? 4.0 : 2.0;
+    cir_prof_begin(ctx, CIR_PROF_LAYERNORM, (double)rows * D * ((x_f32 ? 4.0 : es) + (res ? es : 0.0) + (y_f32 ? 4.0 : es)));
+  }
 #define LN_LAUNCH(TX, TR, TY) \
   add_layernorm_kernel<TX, TR, TY><<<grid, block, 0, ctx->stream>>>((const TX*)x, x_rows, (const TR*)res, gamma, beta, rows_per_group, (TY*)y, rows, eps)
   if (f32) LN_LAUNCH(float, float, float);
@@ -235,6 +250,7 @@ extern "C" int cir_add_layernorm(cir_ctx* ctx, const void* x, int x_f32, int64_t
   else if (y_f32) LN_LAUNCH(bf16, bf16, float);
   else LN_LAUNCH(bf16, bf16, bf16);
 #undef LN_LAUNCH
+  cir_prof_end(ctx);
   CIR_LAUNCH_CHECK(ctx);
   return CIR_OK;
 }

@@ -85,6 +85,12 @@ class Engine:
         N.check(self._lib.cir_profile_gemm_read(self.ctx, C.byref(ms), C.byref(fl), C.byref(n)))
         return ms.value, fl.value, n.value
 
+    def profile_read(self, kind: int):
+        """-> (summed ms, summed algorithmic work, launches) of the kernels of ``kind`` (native.PROF_*) since profile_gemm(True)."""
+        ms, wk, n = C.c_double(), C.c_double(), N.i64()
+        N.check(self._lib.cir_profile_read(self.ctx, kind, C.byref(ms), C.byref(wk), C.byref(n)))
+        return ms.value, wk.value, n.value
+
     def launch_count(self, reset: bool = False) -> int:
         return int(self._lib.cir_launch_count(self.ctx, 1 if reset else 0))
 
@@ -357,7 +363,7 @@ class Engine:
         return out
 
     def stage2_score_chunk(self, w, gallery_tokens, cand_list, z_t, ids, mask, trip_query, trip_slot, want_feats=False,
-                           attn_work=None, attn_tiles=None, attn_tiles_cls=None, prefix=None):
+                           attn_work=None, attn_tiles=None, attn_tiles_cls=None, prefix=None, out=None):
         """One C-ABI call: T triplets sharing C candidates -> (scores fp32 [T], feats fp32 [T,1536] | None).
         ``attn_work``: optional int32 [W,4] K/V-sharing work list (schedule.build_attn_work).
         ``prefix``: optional (a0, qc0) from :meth:`stage2_prefix` for the same Q queries as ids/mask (z_t is then unused)."""
@@ -367,7 +373,8 @@ class Engine:
         if prefix is None:
             assert z_t.shape == (Q, L, HIDDEN) and z_t.dtype == self.act_dtype and z_t.is_contiguous()
         assert gallery_tokens.dtype == self.act_dtype and gallery_tokens.is_contiguous()
-        scores = torch.empty(T, dtype=torch.float32, device=self.device)
+        scores = torch.empty(T, dtype=torch.float32, device=self.device) if out is None else out
+        assert scores.is_contiguous() and scores.numel() == T and scores.dtype == torch.float32
         feats = torch.empty(T, 2 * HIDDEN, dtype=torch.float32, device=self.device) if want_feats else None
         need = self._lib.cir_stage2_workspace_bytes(self.ctx, T, Cn, Q, L, n_tok)
         ws = self.workspace(need)
@@ -411,32 +418,86 @@ class Engine:
                 qc0[:, q0 * L:(q0 + nb) * L].copy_(q_b)
         return a0, qc0
 
-    def stage2_score_matrix(self, w, gallery_tokens, z_t, ids, mask, cand_idx, row_active=None):
-        """All Q*K triplets, candidate-major.  z_t act [Q,L,768]; ids/mask [Q,L]; cand_idx [Q,K] ->
-        scores fp32 [Q,K]; inactive rows are filled with -99999.99 (src/validate_stage2.py:123,258).
-        With more than one chunk, layer 0's query-only part is computed once for all Q queries (stage2_prefix) instead of
-        once per chunk for the chunk's unique queries."""
+    def _upload_i32(self, arrays: List[np.ndarray]) -> List[torch.Tensor]:
+        """Many small int32 host arrays -> device tensors with ONE pinned staging copy (one H2D instead of one per array;
+        flat_pos arrays are int64 and travel as int32 pairs).  The staging buffer is reused: the copy that last read it is
+        waited for before it is overwritten."""
+        sizes = [int(a.size) * (2 if a.dtype == np.int64 else 1) for a in arrays]
+        offs = np.concatenate([[0], np.cumsum([(n + 3) & ~3 for n in sizes])]).astype(np.int64)      # 16 B aligned slices
+        total = int(offs[-1])
+        if total == 0:
+            return [torch.empty(a.shape, dtype=torch.int64 if a.dtype == np.int64 else torch.int32, device=self.device) for a in arrays]
+        if getattr(self, "_stage_host", None) is None or self._stage_host.numel() < total:
+            self._stage_host = torch.empty(max(total, 1 << 20), dtype=torch.int32).pin_memory()
+            self._stage_event = None
+        if self._stage_event is not None:
+            self._stage_event.synchronize()
+        host = self._stage_host.numpy()
+        for a, o, n in zip(arrays, offs[:-1], sizes):
+            if n:
+                host[o:o + n] = np.ascontiguousarray(a).reshape(-1).view(np.int32)
+        dev = self._stage_host[:total].to(self.device, non_blocking=True)
+        self._stage_event = torch.cuda.Event()
+        self._stage_event.record(torch.cuda.current_stream(self.device))
+        self.h2d_bytes = getattr(self, "h2d_bytes", 0) + total * 4
+        out = []
+        for a, o, n in zip(arrays, offs[:-1], sizes):
+            t = dev[o:o + n]
+            out.append(t.view(torch.int64).view(a.shape) if a.dtype == np.int64 else t.view(a.shape))
+        return out
+
+    def stage2_score_pairs(self, w, gallery_tokens, z_t, ids, mask, cand_idx, row_active=None, part=None):
+        """Score this process's share of the Q*K triplets, candidate-major.  ``part=(rank, world)`` restricts the work to the
+        rank's contiguous candidate range (schedule.candidate_partition): every candidate's K/V projections stay on ONE rank,
+        so the per-GPU K/V reuse does not fall with the number of GPUs.  z_t act [Q,L,768] / ids / mask [Q,L] cover ALL Q queries.
+        -> (flat_pos int64 [n] = q*K+k of each scored triplet, scores fp32 [n]) on the device."""
         cand_np = cand_idx.cpu().numpy() if isinstance(cand_idx, torch.Tensor) else np.asarray(cand_idx)
         Q, K = cand_np.shape
         self._check_range(cand_np, gallery_tokens.shape[0], "stage2_score_matrix cand_idx")
         self._check_range(ids, getattr(self, "vocab_rows", None), "stage2_score_matrix token ids")
         act_np = None if row_active is None else np.asarray(row_active, dtype=bool)
-        chunks = plan_chunks(cand_np, act_np, self.max_triplets, self.max_candidates)
-        out = torch.full((Q * K,), NEG_FILL, dtype=torch.float32, device=self.device)
+        info: dict = {}
+        chunks = plan_chunks(cand_np, act_np, self.max_triplets, self.max_candidates, part=part, info=info)
+        self.last_plan = {"part_sizes": info["part_sizes"], "chunks": len(chunks), "triplets": int(sum(c.flat_pos.size for c in chunks)),
+                          "candidate_loads": int(sum(c.cand_list.size for c in chunks))}
         ids_d, mask_d = self._i32(ids), self._i32(mask)
         L = ids_d.shape[1]
-        prefix = self.stage2_prefix(w, z_t, ids_d, mask_d) if (self.query_prefix and len(chunks) > 1) else None
+        if not chunks:
+            return (torch.empty(0, dtype=torch.int64, device=self.device), torch.empty(0, dtype=torch.float32, device=self.device))
+        use_prefix = self.query_prefix and len(chunks) > 1
+        # every index array of every chunk in one upload
+        host: List[np.ndarray] = []
         for ch in chunks:
-            lists = dict(attn_work=build_attn_work(ch.trip_slot, L), attn_tiles=build_attn_tiles(ch.trip_slot, L),
-                         attn_tiles_cls=build_attn_tiles(ch.trip_slot, 1))
+            tq = ch.query_list[ch.trip_query] if use_prefix else ch.trip_query     # prefix: global query rows
+            host += [ch.cand_list, tq.astype(np.int32), ch.trip_slot, build_attn_work(ch.trip_slot, L), build_attn_tiles(ch.trip_slot, L),
+                     build_attn_tiles(ch.trip_slot, 1), ch.flat_pos, ch.query_list.astype(np.int64)]
+        dev = self._upload_i32(host)
+        prefix = self.stage2_prefix(w, z_t, ids_d, mask_d) if use_prefix else None
+        scores = torch.empty(self.last_plan["triplets"], dtype=torch.float32, device=self.device)
+        pos = torch.empty(self.last_plan["triplets"], dtype=torch.int64, device=self.device)
+        o = 0
+        for i, ch in enumerate(chunks):
+            cl, tq, ts, aw, at, ac, fp, ql = dev[8 * i:8 * i + 8]
+            lists = dict(attn_work=aw, attn_tiles=at, attn_tiles_cls=ac)
+            n = ch.flat_pos.size
             if prefix is not None:                              # global query rows: no per-chunk selection of z_t / ids / mask
-                s, _ = self.stage2_score_chunk(w, gallery_tokens, ch.cand_list, None, ids_d, mask_d, ch.query_list[ch.trip_query],
-                                               ch.trip_slot, prefix=prefix, **lists)
+                s, _ = self.stage2_score_chunk(w, gallery_tokens, cl, None, ids_d, mask_d, tq, ts, prefix=prefix, out=scores[o:o + n], **lists)
             else:
-                ql = torch.from_numpy(ch.query_list.astype(np.int64)).to(self.device)
-                s, _ = self.stage2_score_chunk(w, gallery_tokens, ch.cand_list, z_t.index_select(0, ql).contiguous(),
-                                               ids_d.index_select(0, ql), mask_d.index_select(0, ql), ch.trip_query, ch.trip_slot, **lists)
-            out.index_copy_(0, torch.from_numpy(ch.flat_pos).to(self.device), s)
+                s, _ = self.stage2_score_chunk(w, gallery_tokens, cl, z_t.index_select(0, ql).contiguous(), ids_d.index_select(0, ql),
+                                               mask_d.index_select(0, ql), tq, ts, out=scores[o:o + n], **lists)
+            pos[o:o + n] = fp
+            o += n
+        return pos, scores
+
+    def stage2_score_matrix(self, w, gallery_tokens, z_t, ids, mask, cand_idx, row_active=None):
+        """All Q*K triplets, candidate-major.  z_t act [Q,L,768]; ids/mask [Q,L]; cand_idx [Q,K] ->
+        scores fp32 [Q,K]; inactive rows are filled with -99999.99 (src/validate_stage2.py:123,258).
+        With more than one chunk, layer 0's query-only part is computed once for all Q queries (stage2_prefix) instead of
+        once per chunk for the chunk's unique queries."""
+        Q, K = cand_idx.shape
+        pos, s = self.stage2_score_pairs(w, gallery_tokens, z_t, ids, mask, cand_idx, row_active)
+        out = torch.full((Q * K,), NEG_FILL, dtype=torch.float32, device=self.device)
+        out.index_copy_(0, pos, s)
         return out.view(Q, K)
 
     # ------------------------------------------------------------------ sort / top-K / recall
@@ -510,7 +571,8 @@ class Engine:
                 "cir_topk_merge")
         return td, ti
 
-    def recall_counts(self, labels: torch.Tensor, order: torch.Tensor, ks: Sequence[int]) -> List[int]:
+    def recall_counts(self, labels: torch.Tensor, order: torch.Tensor, ks: Sequence[int], sync: bool = True):
+        """-> hit counts per k: a python list (device -> host read, synchronises) or, with sync=False, the int64 device tensor."""
         labels = labels.to(self.device).to(torch.uint8).contiguous()
         order = order.to(self.device, torch.int32).contiguous()
         Q, K = labels.shape
@@ -518,7 +580,7 @@ class Engine:
         arr = (N.i32 * len(ks))(*[int(k) for k in ks])
         self._sync_stream()
         N.check(self._lib.cir_recall_counts(self.ctx, N.ptr(labels), N.ptr(order), Q, K, arr, len(ks), N.ptr(hits)), "cir_recall_counts")
-        return hits.cpu().tolist()
+        return hits.cpu().tolist() if sync else hits
 
     # ------------------------------------------------------------------ primitive ops (tests)
     def gemm(self, A, W, bias=None, residual=None, act=N.ACT_NONE, out_f32=False, ln=None):

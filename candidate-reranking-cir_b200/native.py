@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("CIR_B200_LIB") or os.path.join(HERE, "csrc", "libcir_
 DTYPE_F32, DTYPE_BF16 = 0, 1
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_TCGEN05_1CTA = 0, 1, 2, 3
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+PROF_GEMM, PROF_ATTN_TC, PROF_ATTN_SELF, PROF_LAYERNORM, PROF_QKV_ATTN = 0, 1, 2, 3, 4
 LAYERS = 12
 
 vp = C.c_void_p
@@ -96,6 +97,7 @@ _SIGS = {
     "cir_get_dtype": (C.c_int, [vp]),
     "cir_launch_count": (i64, [vp, C.c_int]),
     "cir_profile_gemm": (C.c_int, [vp, C.c_int]),
+    "cir_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]),
     "cir_profile_gemm_read": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]),
     "cir_gemm": (C.c_int, [vp, C.POINTER(GemmArgs)]),
     "cir_add_layernorm": (C.c_int, [vp, vp, C.c_int, i64, vp, vp, vp, i64, vp, C.c_int, i64, C.c_float]),

@@ -17,6 +17,20 @@ def _name_index(index_names):
     return {n: i for i, n in enumerate(index_names)}
 
 
+def _names_to_rows(index_names, n2i, names) -> np.ndarray:
+    """[Q,K] array of image names -> gallery rows (the reference does this with per-query itemgetter lookups,
+    src/validate_stage2.py:111-116,251); one hash join for the whole matrix."""
+    names = np.asarray(names)
+    try:
+        import pandas as pd
+        rows = pd.Index(index_names).get_indexer(names.reshape(-1))
+        if (rows < 0).any():
+            raise KeyError(str(names.reshape(-1)[np.flatnonzero(rows < 0)[0]]))
+        return rows.astype(np.int32).reshape(names.shape)
+    except ImportError:                                           # pragma: no cover
+        return np.vectorize(n2i.__getitem__, otypes=[np.int32])(names)
+
+
 def _percent(count: int, total: int) -> float:
     # (torch.sum(labels[:, :k]) / len(labels)).item() * 100   (src/validate_stage2.py:60-62,196-203)
     return (torch.tensor(int(count)) / total).item() * 100
@@ -60,23 +74,25 @@ def _predict(blip_model, model_stage1, dataset, index_names, index_features, cap
     eng = blip_model.engine
     n2i = _name_index(index_names)
     ref_idx = np.array([n2i[n] for n in dataset.reference_names], dtype=np.int32)
-    to_idx = np.vectorize(n2i.__getitem__, otypes=[np.int32])
-    cand_idx = to_idx(np.asarray(cand_names))
-    extra_idx = None if extra_cand_names is None else to_idx(np.asarray(extra_cand_names))
+    cand_idx = _names_to_rows(index_names, n2i, cand_names)
+    extra_idx = None if extra_cand_names is None else _names_to_rows(index_names, n2i, extra_cand_names)
     ids, mask = _tokens(blip_model, dataset, captions)
     gallery = eng.to_act(index_features)
     Q = cand_idx.shape[0]
     scores = torch.empty(Q, cand_idx.shape[1], dtype=torch.float32, device=eng.device)
     extra = None if extra_idx is None else torch.empty(Q, extra_idx.shape[1], dtype=torch.float32, device=eng.device)
     active = np.ones(Q, bool) if row_active is None else np.asarray(row_active, bool)
+    from .distributed import encode_queries_sharded, score_matrix_sharded
     for rows, L in _length_buckets(mask, LENGTH_BUCKET):
         r_t = torch.from_numpy(rows).to(eng.device)
         ids_b, mask_b = ids[r_t, :L].contiguous(), mask[r_t, :L].contiguous()
-        # z_t from the frozen stage-I encoder on the reference image's tokens (src/validate_stage2.py:105-106,243-244)
-        z_t, _ = model_stage1.encode_queries(gallery, ref_idx[rows], ids_b, mask_b, want_z=True, want_emb=False)
-        scores[r_t] = blip_model.score_triplets(z_t, ids_b, mask_b, gallery, cand_idx[rows], active[rows])
+        # z_t from the frozen stage-I encoder on the reference image's tokens (src/validate_stage2.py:105-106,243-244).
+        # Under torch.distributed (one process per GPU) the queries' z_t and the candidate ranges are split over the ranks
+        # and every rank ends up with the full score rows; single-process: plain calls.
+        z_t = encode_queries_sharded(model_stage1, gallery, ref_idx[rows], ids_b, mask_b)
+        scores[r_t] = score_matrix_sharded(blip_model, gallery, z_t, ids_b, mask_b, cand_idx[rows], active[rows])
         if extra is not None:
-            extra[r_t] = blip_model.score_triplets(z_t, ids_b, mask_b, gallery, extra_idx[rows], None)
+            extra[r_t] = score_matrix_sharded(blip_model, gallery, z_t, ids_b, mask_b, extra_idx[rows], None)
     return scores, extra
 
 
@@ -89,14 +105,17 @@ def generate_fiq_val_predictions(blip_model, model_stage1, relative_val_dataset,
     return logits, list(relative_val_dataset.target_names)
 
 
-def compute_fiq_val_metrics(relative_val_dataset, blip_model, model_stage1, index_features, index_names) -> Tuple[float, float]:
-    """src/validate_stage2.py:33-66 -> (recall@10, recall@50)."""
+def compute_fiq_val_metrics(relative_val_dataset, blip_model, model_stage1, index_features, index_names, return_order: bool = False):
+    """src/validate_stage2.py:33-66 -> (recall@10, recall@50).  ``return_order=True`` appends the re-ranked order [Q,K] as a
+    HOST int32 array -- the ``sorted_indices`` the reference brings to the CPU at :53."""
     predicted_logits, _ = generate_fiq_val_predictions(blip_model, model_stage1, relative_val_dataset, index_names, index_features)
     eng = blip_model.engine
     order = eng.rerank_sort(predicted_logits)                                       # argsort descending (:53)
     labels = torch.from_numpy(np.asarray(relative_val_dataset.K_labels))
     h10, h50 = eng.recall_counts(labels, order, (10, 50))                           # take_along_axis + sums (:56-61)
     Q = len(labels)
+    if return_order:
+        return _percent(h10, Q), _percent(h50, Q), order.cpu().numpy()
     return _percent(h10, Q), _percent(h50, Q)
 
 

@@ -88,6 +88,16 @@ int64_t cir_launch_count(cir_ctx* ctx, int reset);
  * returns summed duration, summed algorithmic FLOPs (2*M*N*K*batch) and the launch count. */
 int  cir_profile_gemm(cir_ctx* ctx, int enable);
 int  cir_profile_gemm_read(cir_ctx* ctx, double* total_ms, double* total_flops, int64_t* launches);
+/* the same event pairs are recorded around the other kernels that matter for the step time; `kind` selects them:
+ * total_work = algorithmic FLOPs for CIR_PROF_GEMM / CIR_PROF_ATTN_TC (4*Lq*Lk*64 per (batch, head)) / CIR_PROF_ATTN_SELF /
+ * CIR_PROF_QKV_ATTN (projection + attention), algorithmic bytes (rows * 768 * (bytes read + bytes written)) for CIR_PROF_LAYERNORM. */
+#define CIR_PROF_GEMM      0
+#define CIR_PROF_ATTN_TC   1   /* tcgen05 cross-attention / ViT attention */
+#define CIR_PROF_ATTN_SELF 2   /* masked text self-attention (mma.sync kernels) */
+#define CIR_PROF_LAYERNORM 3
+#define CIR_PROF_QKV_ATTN  4   /* fused QKV projection + masked self-attention */
+#define CIR_PROF_KINDS     5
+int  cir_profile_read(cir_ctx* ctx, int kind, double* total_ms, double* total_work, int64_t* launches);
 
 /* ---- primitive ops (each replaces one ATen call of the reference; used by the pipelines
  *      below and individually by the parity tests) ------------------------------------- */

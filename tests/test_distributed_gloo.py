@@ -67,6 +67,33 @@ def _worker(rank, ws, port, ret):
         # empty shard: 1 query over 2 ranks
         one = D.sharded_stage2_scores(lambda rows: full[:1][rows].clone(), 1)
         assert torch.equal(one, full[:1])
+        # ---- stage II, candidate-range partition: each rank scores the triplets of its candidate range, ranks exchange
+        #      (flat position, score) pairs, inactive rows keep the fill value
+        S = cir.schedule
+        Qc, Kc, Gc = 23, 7, 11
+        rng = np.random.default_rng(5)
+        cand = np.stack([rng.permutation(Gc)[:Kc] for _ in range(Qc)]).astype(np.int32)
+        active = rng.random(Qc) < 0.8
+        truth = torch.randn(Qc, Kc, generator=g)
+        seen_cands = {}
+
+        def pairs(part):
+            assert part == (rank, ws)
+            info = {}
+            chunks = S.plan_chunks(cand, active, 16, 3, part=part, info=info)
+            pos = np.concatenate([c.flat_pos for c in chunks]) if chunks else np.zeros(0, np.int64)
+            seen_cands[rank] = set(np.concatenate([c.cand_list for c in chunks]).tolist()) if chunks else set()
+            return torch.from_numpy(pos), truth.reshape(-1)[torch.from_numpy(pos)], info["part_sizes"]
+        full2 = D.sharded_stage2_scores_by_candidate(pairs, Qc, Kc, -99999.99)
+        want = truth.clone()
+        want[~torch.from_numpy(active)] = -99999.99
+        assert torch.equal(full2, want)
+        # no gallery image is owned by two ranks
+        mine = torch.zeros(Gc, dtype=torch.int64)
+        mine[list(seen_cands[rank])] = 1
+        both = [torch.zeros_like(mine) for _ in range(ws)]
+        dist.all_gather(both, mine)
+        assert int((both[0] * both[1]).sum()) == 0 and int((both[0] + both[1]).sum()) == len(set(cand[active].reshape(-1).tolist()))
         ret[rank] = "ok"
     except Exception as e:  # pragma: no cover
         ret[rank] = f"{type(e).__name__}: {e}"

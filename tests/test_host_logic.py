@@ -173,3 +173,39 @@ def test_layernorm_folding_identity():
     rstd = (var + eps).rsqrt()
     got = rstd * (x @ Wf.T) - rstd * mu * colsum[None, :] + bf[None, :]
     assert (got - want).abs().max() < 1e-10
+
+
+def test_candidate_partition_and_balanced_chunks():
+    from importlib import import_module
+    sched = import_module("candidate-reranking-cir_b200.schedule")
+    rng = np.random.default_rng(1)
+    Q, K, G = 301, 20, 97
+    cand = np.stack([rng.permutation(G)[:K] for _ in range(Q)]).astype(np.int32)
+    active = rng.random(Q) < 0.9
+    want = np.flatnonzero(np.repeat(active, K))
+    for world in (1, 2, 3, 8):
+        seen, owners, infos = [], {}, []
+        for r in range(world):
+            info = {}
+            chunks = sched.plan_chunks(cand, active, 512, 16, part=(r, world), info=info)
+            infos.append(info["part_sizes"])
+            assert sum(c.flat_pos.size for c in chunks) == info["part_sizes"][r]
+            for c in chunks:
+                assert c.flat_pos.size <= 512 and c.cand_list.size <= 16
+                seen.append(c.flat_pos)
+                for g in c.cand_list.tolist():
+                    assert owners.setdefault(g, r) == r, "a candidate's triplets must stay on one rank"
+        assert all(i == infos[0] for i in infos)                                     # every rank derives the same partition
+        assert np.array_equal(np.sort(np.concatenate(seen)), want)
+        sizes = np.array(infos[0])
+        assert sizes.max() - sizes.min() <= 2 * np.bincount(cand[active].reshape(-1)).max()    # cut moved by at most one candidate run
+    # balanced chunks: no small tail chunk
+    chunks = sched.plan_chunks(cand, active, 512, 64)
+    sizes = np.array([c.flat_pos.size for c in chunks])
+    assert sizes.min() > 0.8 * sizes.max()
+    greedy = sched.plan_chunks(cand, active, 512, 64, balance=False)
+    assert np.array_equal(np.sort(np.concatenate([c.flat_pos for c in greedy])), want)
+    # wide candidate ids (no 16-bit radix fast path)
+    big = cand.astype(np.int64) * 1000
+    a = sched.plan_chunks(big, active, 512, 16)
+    assert np.array_equal(np.sort(np.concatenate([c.flat_pos for c in a])), want)
