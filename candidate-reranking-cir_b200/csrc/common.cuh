@@ -21,6 +21,7 @@ struct cir_ctx {
   int prune_last;       // 1 = stage II computes the last layer for the CLS rows only (default)
   int gemm_tma_store;   // 1 = bf16 GEMM outputs leave through TMA bulk tensor stores (default)
   int virtual_ln;       // 1 = stage-II self / FFN LayerNorms are never materialised (cir_gemm_ln), when the weights carry folded copies
+  int fuse_qkv;         // 1 = QKV projection + masked text self-attention as one kernel where eligible (default)
   int dedup_first;      // 1 = stage II runs layer 0's query-only part once per unique query of a chunk (default)
   unsigned func_attr_mask;   // kernels whose dynamic shared-memory limit was raised on this context's device (bit per kernel)
   int fuse_ln;          // 1 = LayerNorm fused into the N=768 pair-tile GEMM epilogues where eligible (default)
@@ -119,5 +120,6 @@ int cir_make_map_2d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t ro
 int cir_make_map_3d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1, int64_t s2,
                     int b0, int b1, int b2);
 int cir_attention_tc(cir_ctx* ctx, const cir_attn_args* a);
+bool cir_qkv_attention_supported(const cir_ctx* ctx, int64_t L);   // qkv_attention.cu
 // true when cir_gemm_tcgen05 would use the cta_group::2 pair tile for this shape (the fused LayerNorm needs it)
 bool cir_gemm_uses_pair(const cir_ctx* ctx, int64_t M, int64_t N, int batch);    // attention_tc.cu; CIR_EUNSUPPORTED -> caller falls back

@@ -75,6 +75,7 @@ extern "C" int cir_create(cir_ctx** out, int device, int dtype) {
   c->gemm_pair = 1;
   c->prune_last = 1;
   c->dedup_first = 1;
+  c->fuse_qkv = 1;
   c->gemm_tma_store = 1;
   c->func_attr_mask = 0;
   c->virtual_ln = 0;
@@ -137,6 +138,7 @@ extern "C" int cir_set_attention_impl(cir_ctx* ctx, int impl) {
 }
 extern "C" int cir_set_prune_last_layer(cir_ctx* ctx, int enable) { ctx->prune_last = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_set_dedup_first_layer(cir_ctx* ctx, int enable) { ctx->dedup_first = enable ? 1 : 0; return CIR_OK; }
+extern "C" int cir_set_fuse_qkv_attention(cir_ctx* ctx, int enable) { ctx->fuse_qkv = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_set_fuse_layernorm(cir_ctx* ctx, int enable) { ctx->fuse_ln = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_set_virtual_layernorm(cir_ctx* ctx, int enable) { ctx->virtual_ln = enable; return CIR_OK; }   // 1 both, 2 self-LN only, 3 FFN-LN only
 extern "C" int cir_set_gemm_tma_store(cir_ctx* ctx, int enable) { ctx->gemm_tma_store = enable ? 1 : 0; return CIR_OK; }
@@ -213,6 +215,32 @@ constexpr float BERT_EPS = 1e-12f;   // configs/med_config.json:11
 constexpr float VIT_EPS = 1e-6f;     // src/vit.py:142
 
 }  // namespace
+
+// ctx_s = softmax(Q K^T / 8 + mask) V of the text self-attention of `batch` streams (captions x L rows each, stream stride
+// caps*L rows in hin / qkv / ctxout), Q|K|V = hin Wqkv^T + b.  bf16 with L = 16 / 32: one fused kernel (the projection never
+// reaches HBM); otherwise the QKV GEMM into `qkv` followed by one attention call per stream.
+static int self_attention(cir_ctx* ctx, const void* hin, const void* wqkv, const float* bqkv, int batch, const int32_t* mask,
+                          const int32_t* mask_index, int64_t caps, int64_t L, void* qkv, void* ctxout) {
+  const size_t es = act_size(ctx);
+  const int64_t Mr = caps * L;
+  if (ctx->fuse_qkv && cir_qkv_attention_supported(ctx, L)) {
+    cir_qkv_attn_args q{};
+    q.x = hin; q.x_bs = Mr * D; q.w = wqkv; q.bias = bqkv; q.out = ctxout; q.out_rs = D; q.out_bs = Mr * D;
+    q.key_mask = mask; q.mask_index = mask_index; q.captions = caps; q.L = (int32_t)L; q.batch = batch; q.scale = 0.125f;
+    return cir_qkv_attention(ctx, &q);
+  }
+  CIR_TRY(gemm(ctx, hin, D, Mr * D, wqkv, D, 3 * D * D, bqkv, 3 * D, qkv, 3 * D, Mr * 3 * D, 0, nullptr, 0, 0, 0, Mr, 3 * D, D, batch, CIR_ACT_NONE));
+  for (int s = 0; s < batch; s++) {
+    cir_attn_args a{};
+    void* qkv_s = at(qkv, s * Mr * 3 * D, es);
+    a.q = qkv_s; a.k = at(qkv_s, D, es); a.v = at(qkv_s, 2 * D, es); a.o = at(ctxout, s * Mr * D, es);
+    a.q_bs = a.k_bs = a.v_bs = L * 3 * D; a.q_rs = a.k_rs = a.v_rs = 3 * D; a.o_bs = L * D; a.o_rs = D;
+    a.key_mask = mask; a.mask_index = mask_index;
+    a.B = (int32_t)caps; a.H = CIR_HEADS; a.Lq = (int32_t)L; a.Lk = (int32_t)L; a.scale = 0.125f;                   // / sqrt(64) (nlvr_encoder.py:193)
+    CIR_TRY(cir_attention(ctx, &a));
+  }
+  return CIR_OK;
+}
 
 // ========================================================================================== ViT
 struct VitWs { void *patches, *patch_out, *x, *y, *qkv, *ctx, *f; size_t total; };
@@ -317,12 +345,7 @@ extern "C" int cir_stage1_encode(cir_ctx* ctx, const cir_stage1_weights* w, cons
   CIR_TRY(cir_gather_rows(ctx, gallery_tokens, ref_index, ws.reft, Q, N * D));
   CIR_TRY(cir_bert_embeddings(ctx, ids, Q, L, w->word_emb, w->pos_emb, w->emb_ln_g, w->emb_ln_b, ws.h));         // med.py:86-110
   for (int i = 0; i < CIR_LAYERS; i++) {                                                                           // med.py:348-398
-    CIR_TRY(gemm(ctx, ws.h, D, 0, w->self_qkv_w[i], D, 0, w->self_qkv_b[i], 0, ws.qkv, 3 * D, 0, 0, nullptr, 0, 0, 0, R, 3 * D, D, 1, CIR_ACT_NONE));
-    cir_attn_args a{};
-    a.q = ws.qkv; a.k = at(ws.qkv, D, es); a.v = at(ws.qkv, 2 * D, es); a.o = ws.ctx;
-    a.q_bs = a.k_bs = a.v_bs = L * 3 * D; a.q_rs = a.k_rs = a.v_rs = 3 * D; a.o_bs = L * D; a.o_rs = D;
-    a.key_mask = mask; a.B = (int32_t)Q; a.H = CIR_HEADS; a.Lq = (int32_t)L; a.Lk = (int32_t)L; a.scale = 0.125f;
-    CIR_TRY(cir_attention(ctx, &a));
+    CIR_TRY(self_attention(ctx, ws.h, w->self_qkv_w[i], w->self_qkv_b[i], 1, mask, nullptr, Q, L, ws.qkv, ws.ctx));   // med.py:112-216
     CIR_TRY(gemm(ctx, ws.ctx, D, 0, w->self_out_w[i], D, 0, w->self_out_b[i], 0, ws.pre, D, 0, 0, ws.h, D, 0, 0, R, D, D, 1, CIR_ACT_NONE));
     CIR_TRY(cir_add_layernorm(ctx, ws.pre, 0, R, nullptr, w->self_ln_g[i], w->self_ln_b[i], R, ws.a, 0, R, BERT_EPS));
     // cross-attention onto the reference image tokens (all-ones encoder mask -> +0)
@@ -393,17 +416,7 @@ static int stage2_query_block(cir_ctx* ctx, const cir_stage2_weights* w, const v
                               void* qkv, void* ctxbuf, void* scratch, void* a_out, void* qc_out) {
   const size_t es = act_size(ctx);
   const int64_t Mq = Q * L;
-  CIR_TRY(gemm(ctx, hq, D, Mq * D, w->self_qkv_w[0], D, 3 * D * D, w->self_qkv_b[0], 3 * D, qkv, 3 * D, Mq * 3 * D, 0,
-               nullptr, 0, 0, 0, Mq, 3 * D, D, 2, CIR_ACT_NONE));
-  for (int s = 0; s < 2; s++) {
-    cir_attn_args a{};
-    void* qkv_s = at(qkv, s * Mq * 3 * D, es);
-    a.q = qkv_s; a.k = at(qkv_s, D, es); a.v = at(qkv_s, 2 * D, es); a.o = at(ctxbuf, s * Mq * D, es);
-    a.q_bs = a.k_bs = a.v_bs = L * 3 * D; a.q_rs = a.k_rs = a.v_rs = 3 * D; a.o_bs = L * D; a.o_rs = D;
-    a.key_mask = mask;                                       // mask row q belongs to query q
-    a.B = (int32_t)Q; a.H = CIR_HEADS; a.Lq = (int32_t)L; a.Lk = (int32_t)L; a.scale = 0.125f;
-    CIR_TRY(cir_attention(ctx, &a));
-  }
+  CIR_TRY(self_attention(ctx, hq, w->self_qkv_w[0], w->self_qkv_b[0], 2, mask, nullptr, Q, L, qkv, ctxbuf));   // mask row q belongs to query q
   CIR_TRY(gemm_layernorm(ctx, ctxbuf, D, Mq * D, w->self_out_w[0], D, D * D, w->self_out_b[0], D, hq, D, Mq * D,
                          w->self_ln_g[0], w->self_ln_b[0], BERT_EPS, scratch, a_out, Mq, D, 2));
   return gemm(ctx, a_out, D, Mq * D, w->cross_q_w[0], D, D * D, w->cross_q_b[0], D, qc_out, D, Mq * D, 0, nullptr, 0, 0, 0,
@@ -509,17 +522,18 @@ static int stage2_score_impl(cir_ctx* ctx, const cir_stage2_weights* w, const vo
       CIR_TRY(gemm(ctx, ws.h, D, M * D, w->vq_w[i], D, 3 * D * D, w->vq_b[i], 3 * D, ws.qkv, 3 * D, M * 3 * D, 0,
                    nullptr, 0, 0, 0, M, 3 * D, D, 2, CIR_ACT_NONE, &e));
     } else {
-      CIR_TRY(gemm(ctx, ws.h, D, M * D, w->self_qkv_w[i], D, 3 * D * D, w->self_qkv_b[i], 3 * D, ws.qkv, 3 * D, M * 3 * D, 0,
-                   nullptr, 0, 0, 0, M, 3 * D, D, 2, CIR_ACT_NONE));
+      CIR_TRY(self_attention(ctx, ws.h, w->self_qkv_w[i], w->self_qkv_b[i], 2, mask, trip_query, T, L, ws.qkv, ws.ctx));
     }
-    for (int s = 0; s < 2; s++) {
-      cir_attn_args a{};
-      void* qkv_s = at(ws.qkv, s * M * 3 * D, es);
-      a.q = qkv_s; a.k = at(qkv_s, D, es); a.v = at(qkv_s, 2 * D, es); a.o = at(ws.ctx, s * M * D, es);
-      a.q_bs = a.k_bs = a.v_bs = L * 3 * D; a.q_rs = a.k_rs = a.v_rs = 3 * D; a.o_bs = L * D; a.o_rs = D;
-      a.key_mask = mask; a.mask_index = trip_query;
-      a.B = (int32_t)T; a.H = CIR_HEADS; a.Lq = (int32_t)L; a.Lk = (int32_t)L; a.scale = 0.125f;                  // / sqrt(64) (:193)
-      CIR_TRY(cir_attention(ctx, &a));
+    if (h_raw) {
+      for (int s = 0; s < 2; s++) {
+        cir_attn_args a{};
+        void* qkv_s = at(ws.qkv, s * M * 3 * D, es);
+        a.q = qkv_s; a.k = at(qkv_s, D, es); a.v = at(qkv_s, 2 * D, es); a.o = at(ws.ctx, s * M * D, es);
+        a.q_bs = a.k_bs = a.v_bs = L * 3 * D; a.q_rs = a.k_rs = a.v_rs = 3 * D; a.o_bs = L * D; a.o_rs = D;
+        a.key_mask = mask; a.mask_index = trip_query;
+        a.B = (int32_t)T; a.H = CIR_HEADS; a.Lq = (int32_t)L; a.Lk = (int32_t)L; a.scale = 0.125f;                  // / sqrt(64) (:193)
+        CIR_TRY(cir_attention(ctx, &a));
+      }
     }
     // a_s = LayerNorm{A,B}(dense_s(ctx_s) + h_s)   (:261-264)
     if (vln1 || h_raw) {                                       // ws.a = raw dense_s(ctx_s) + h_s, st1 = its row statistics

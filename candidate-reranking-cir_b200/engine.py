@@ -68,6 +68,10 @@ class Engine:
         """stage II: layer 0's query-only part once per unique query of a chunk (default on; exact)."""
         N.check(self._lib.cir_set_dedup_first_layer(self.ctx, 1 if enable else 0))
 
+    def set_fuse_qkv_attention(self, enable: bool):
+        """bf16, L = 16 / 32: QKV projection + masked text self-attention as one kernel (default on; bit-equal to the unfused path)."""
+        N.check(self._lib.cir_set_fuse_qkv_attention(self.ctx, 1 if enable else 0))
+
     def set_virtual_layernorm(self, enable: bool):
         """stage II: never materialise the self-attention / FFN LayerNorms (cir_gemm_ln); bf16 only."""
         N.check(self._lib.cir_set_virtual_layernorm(self.ctx, int(enable)))
@@ -656,6 +660,25 @@ class Engine:
         self._sync_stream()
         N.check(self._lib.cir_attention(self.ctx, C.byref(a)), "cir_attention")
         return o
+
+    def qkv_attention(self, x, w, bias=None, key_mask=None, mask_index=None, scale=0.125):
+        """x [batch, captions, L, 768] bf16, w [batch, 2304, 768] bf16 (query | key | value rows), bias [batch, 2304] fp32,
+        key_mask int [*, L] -> context [batch, captions, L, 768]; test hook over cir_qkv_attention."""
+        nb, caps, L, HD = x.shape
+        assert HD == HIDDEN and w.shape == (nb, 3 * HIDDEN, HIDDEN)
+        x, w = x.contiguous(), w.contiguous()
+        out = torch.empty_like(x)
+        b = None if bias is None else bias.float().contiguous()
+        km = None if key_mask is None else self._i32(key_mask)
+        mi = None if mask_index is None else self._i32(mask_index)
+        a = N.QkvAttnArgs()
+        a.x, a.x_bs, a.w, a.bias = N.ptr(x), caps * L * HD, N.ptr(w), N.ptr(b)
+        a.out, a.out_rs, a.out_bs = N.ptr(out), HD, caps * L * HD
+        a.key_mask, a.mask_index = N.ptr(km), N.ptr(mi)
+        a.captions, a.L, a.batch, a.scale = caps, L, nb, scale
+        self._sync_stream()
+        N.check(self._lib.cir_qkv_attention(self.ctx, C.byref(a)), "cir_qkv_attention")
+        return out
 
     def add_layernorm(self, x, gamma, beta, res=None, x_rows=None, rows_per_group=None, eps=1e-12, out_f32=False):
         rows = (res.shape[0] if res is not None else x.shape[0])

@@ -50,6 +50,11 @@ class AttnArgs(C.Structure):
                 ("B", i32), ("H", i32), ("Lq", i32), ("Lk", i32), ("scale", C.c_float)]
 
 
+class QkvAttnArgs(C.Structure):
+    _fields_ = [("x", vp), ("x_bs", i64), ("w", vp), ("bias", vp), ("out", vp), ("out_rs", i64), ("out_bs", i64),
+                ("key_mask", vp), ("mask_index", vp), ("captions", i64), ("L", i32), ("batch", i32), ("scale", C.c_float)]
+
+
 _A = vp * LAYERS
 
 
@@ -91,6 +96,7 @@ _SIGS = {
     "cir_set_attention_impl": (C.c_int, [vp, C.c_int]),
     "cir_set_prune_last_layer": (C.c_int, [vp, C.c_int]),
     "cir_set_dedup_first_layer": (C.c_int, [vp, C.c_int]),
+    "cir_set_fuse_qkv_attention": (C.c_int, [vp, C.c_int]),
     "cir_set_fuse_layernorm": (C.c_int, [vp, C.c_int]),
     "cir_set_virtual_layernorm": (C.c_int, [vp, C.c_int]),
     "cir_set_gemm_tma_store": (C.c_int, [vp, C.c_int]),
@@ -102,6 +108,7 @@ _SIGS = {
     "cir_gemm": (C.c_int, [vp, C.POINTER(GemmArgs)]),
     "cir_add_layernorm": (C.c_int, [vp, vp, C.c_int, i64, vp, vp, vp, i64, vp, C.c_int, i64, C.c_float]),
     "cir_attention": (C.c_int, [vp, C.POINTER(AttnArgs)]),
+    "cir_qkv_attention": (C.c_int, [vp, C.POINTER(QkvAttnArgs)]),
     "cir_bert_embeddings": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, vp, vp]),
     "cir_gather_rows": (C.c_int, [vp, vp, vp, vp, i64, i64]),
     "cir_cast_f32_to_act": (C.c_int, [vp, vp, vp, i64]),

@@ -110,10 +110,14 @@ def make_stage1_state_dict(seed: int = 0, image_size: int = 384, style: str = "d
 
 
 def make_stage2_state_dict(seed: int = 0, image_size: int = 384, style: str = "dense",
-                           head_gain: float = 1.0) -> Dict[str, torch.Tensor]:
+                           head_gain: float = 1.0, cross_gain: float = 1.0) -> Dict[str, torch.Tensor]:
     """``BLIP_NLVR.state_dict()`` look-alike (src/blip_stage2.py:19-54, twin keys
     as in src/nlvr_encoder.py:225-290). ``head_gain`` scales ``cls_head`` weights so
-    random-init scores are not nearly tied."""
+    random-init scores are not nearly tied.  ``cross_gain`` scales the cross-attention output
+    projections (dense0 / dense1 weights, applied AFTER all random draws so every other tensor is unchanged): with the
+    reference's N(0, 0.02) init the candidate image contributes only a few per cent of the residual stream and the
+    scores of different candidates differ by less than a bf16 implementation's rounding noise; a gain of a few units
+    makes rankings (and Recall@K) a meaningful parity check."""
     ini = _Init(seed * 2 + 12, style)
     sd: Dict[str, torch.Tensor] = {}
     _vit(sd, ini, image_size)
@@ -135,6 +139,10 @@ def make_stage2_state_dict(seed: int = 0, image_size: int = 384, style: str = "d
         ini.layernorm(sd, p + "output.LayerNorm", HIDDEN)
     ini.linear(sd, "cls_head.0", HIDDEN, 2 * HIDDEN, std=0.02 * head_gain)
     ini.linear(sd, "cls_head.2", 2, HIDDEN, std=0.02 * head_gain)
+    if cross_gain != 1.0:
+        for i in range(LAYERS):
+            for s in (0, 1):
+                sd[f"text_encoder.encoder.layer.{i}.crossattention.output.dense{s}.weight"] *= cross_gain
     return sd
 
 

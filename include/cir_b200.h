@@ -71,6 +71,9 @@ int  cir_set_prune_last_layer(cir_ctx* ctx, int enable);
 /* stage II: layer 0's self-attention block and cross query projection depend on the query only (both streams are expanded
  * copies, src/blip_stage2.py:118-124): run them once per unique query of a chunk and expand (default on; exact) */
 int  cir_set_dedup_first_layer(cir_ctx* ctx, int enable);
+/* bf16 mode, captions of 16 or 32 tokens: the query/key/value Linears and the masked text self-attention run as ONE kernel
+ * (cir_qkv_attention) -- the [rows, 2304] projection never reaches HBM.  Default on; 0 = GEMM + attention kernel (bit-equal). */
+int  cir_set_fuse_qkv_attention(cir_ctx* ctx, int enable);
 /* bf16 mode: fuse LayerNorm into the long-K N=768 pair-tile GEMM epilogue (FFN2): statistics in the epilogue, in-place
  * normalisation pass from L2.  Default OFF: measured 53.7k vs 54.4k triplets/s for the separate LayerNorm kernels. */
 int  cir_set_fuse_layernorm(cir_ctx* ctx, int enable);
@@ -173,6 +176,22 @@ typedef struct cir_attn_args {
   float scale;
 } cir_attn_args;
 int cir_attention(cir_ctx* ctx, const cir_attn_args* args);
+
+/* Fused self-attention block input side: out[b][c*L + l, h*64 + d] = softmax(Q_h K_h^T * scale + mask) V_h with
+ * [Q|K|V] = x[b] w[b]^T + bias[b] (query / key / value Linears stacked as [2304, 768], PyTorch [out, in] layout);
+ * replaces BertSelfAttention.forward for text self-attention (src/nlvr_encoder.py:140-222, src/med.py:112-216).
+ * bf16 context only; L in {16, 32}; rows of x / out are caption-major (row = caption*L + token), row stride 768 / out_rs.
+ * key_mask int32 [*, L] (1 = attend, 0 -> additive -10000), row mask_index[c] (NULL: c) belongs to caption c. */
+typedef struct cir_qkv_attn_args {
+  const void* x; int64_t x_bs;          /* [batch][captions*L, 768] bf16; batch stride in elements */
+  const void* w;                        /* [batch][2304, 768] bf16 */
+  const float* bias;                    /* [batch][2304] fp32 or NULL */
+  void* out; int64_t out_rs, out_bs;    /* [batch][captions*L, 768] bf16 context */
+  const int32_t* key_mask; const int32_t* mask_index;
+  int64_t captions; int32_t L; int32_t batch;
+  float scale;
+} cir_qkv_attn_args;
+int cir_qkv_attention(cir_ctx* ctx, const cir_qkv_attn_args* args);
 
 /* out[q,l,:] = LayerNorm(word[ids[q,l]] + pos[l]); src/nlvr_encoder.py:68-91, src/med.py:86-110 */
 int cir_bert_embeddings(cir_ctx* ctx, const int32_t* ids, int64_t Q, int64_t L, const float* word_emb,

@@ -144,7 +144,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     import subprocess
     N = cir.native
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    pairs = {"cir_gemm_args": N.GemmArgs, "cir_gemm_ln": N.GemmLn, "cir_attn_args": N.AttnArgs, "cir_vit_weights": N.VitWeights,
+    pairs = {"cir_gemm_args": N.GemmArgs, "cir_gemm_ln": N.GemmLn, "cir_attn_args": N.AttnArgs, "cir_qkv_attn_args": N.QkvAttnArgs, "cir_vit_weights": N.VitWeights,
              "cir_stage1_weights": N.Stage1Weights, "cir_stage2_weights": N.Stage2Weights}
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "cir_b200.h"\nint main(void) {\n' +

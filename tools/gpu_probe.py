@@ -131,6 +131,24 @@ def attn_probe():
         print(f"cross-attn T={T} L={L} Lk={Lk} runs of ~{T//C}: {name}: {ms:.3f} ms  {flops/ms/1e9:.0f} TF/s (algorithmic)", flush=True)
 
 
+def qkv_probe(T=4096, L=32):
+    """fused QKV + self-attention vs QKV GEMM + attention kernel at the stage-II chunk shape"""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, T, L, 768, generator=g).cuda().bfloat16()
+    w = (torch.randn(2, 2304, 768, generator=g) * 0.04).cuda().bfloat16()
+    bias = torch.randn(2, 2304, generator=g).cuda()
+    mask = torch.ones(T, L, dtype=torch.int32).cuda()
+    flops = 2 * 2 * T * L * 2304 * 768 + 4 * 2 * T * 12 * L * L * 64
+    ms = timeit(lambda: e.qkv_attention(x, w, bias, key_mask=mask), warm=2, it=10)
+    print(f"fused qkv+attention T={T} L={L}: {ms:.3f} ms  {flops/ms/1e9:.0f} TF/s  (CIR_QKV_DEBUG={os.environ.get('CIR_QKV_DEBUG')})", flush=True)
+    x2 = x.reshape(2, T * L, 768)
+    ms_g = timeit(lambda: e.gemm(x2, w, bias), warm=2, it=10)
+    qkv = e.gemm(x2, w, bias)[0].reshape(T, L, 2304)
+    q, k, v = qkv[..., :768], qkv[..., 768:1536], qkv[..., 1536:]
+    ms_a = timeit(lambda: e.attention(q, k, v, key_mask=mask), warm=2, it=10)
+    print(f"unfused: QKV GEMM {ms_g:.3f} ms + 2 x attention {ms_a:.3f} ms = {ms_g + 2 * ms_a:.3f} ms", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "stage2"]
     if "gemm" in which:
@@ -143,5 +161,7 @@ if __name__ == "__main__":
         stage1_probe()
     if "attn" in which:
         attn_probe()
+    if "qkv" in which:
+        qkv_probe()
     if "stage2_profile" in which:      # one short pass for an ncu launch list
         stage2_probe(reps=1, configs=((4096, 64),), Q=96)

@@ -42,9 +42,9 @@ int main() {
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024);
   const int iters = 2000;
   for (int bmn = 0; bmn < 2; bmn++)
-    for (int N : {16, 64, 128, 256})
+    for (int N : {16, 64, 96, 128, 160, 192, 224, 256})
       for (int nacc : {1, 2}) {
-        if (N * nacc > 512) continue;
+        if (N * nacc > 512 || (nacc == 2 && (N & (N - 1)))) continue;
         for (int grid : {1, 148}) {
           k<<<grid, 128, 65536 + 1024>>>(N, nacc, iters, bmn, d);
           cudaError_t e = cudaDeviceSynchronize();
