@@ -22,6 +22,7 @@ struct cir_ctx {
   int gemm_tma_store;   // 1 = bf16 GEMM outputs leave through TMA bulk tensor stores (default)
   int virtual_ln;       // 1 = stage-II self / FFN LayerNorms are never materialised (cir_gemm_ln), when the weights carry folded copies
   int fuse_qkv;         // 1 = QKV projection + masked text self-attention as one kernel where eligible (default)
+  int stage1_tc;        // 1 = stage-I top-K over large galleries filters on the tensor cores, exact fp32 re-check of the survivors (default)
   int dedup_first;      // 1 = stage II runs layer 0's query-only part once per unique query of a chunk (default)
   unsigned func_attr_mask;   // kernels whose dynamic shared-memory limit was raised on this context's device (bit per kernel)
   int fuse_ln;          // 1 = LayerNorm fused into the N=768 pair-tile GEMM epilogues where eligible (default)
@@ -109,6 +110,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Threshold filter of the tcgen05 similarity tiles (stage-I top-K): every accumulator S[row, col] >= thr[row] is appended to the
+// row's candidate list, cand[row * cap + atomicAdd(count[row])] = {col_base + col, float bits of S}; a full list raises *overflow.
+struct cir_gemm_filter {
+  const float* thr; int32_t* count; uint2* cand; int32_t* overflow;
+  int64_t cap; int64_t col_base;
+};
+int cir_gemm_tcgen05_filter(cir_ctx* ctx, const void* A, const void* W, int64_t M, int64_t N, int64_t K, const cir_gemm_filter* f);
+
 // internal cross-file entry points
 int cir_gemm_simt(cir_ctx* ctx, const cir_gemm_args* a);
 int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a);
@@ -121,5 +130,10 @@ int cir_make_map_3d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t d0
                     int b0, int b1, int b2);
 int cir_attention_tc(cir_ctx* ctx, const cir_attn_args* a);
 bool cir_qkv_attention_supported(const cir_ctx* ctx, int64_t L);   // qkv_attention.cu
+// stage1_topk_tc.cu: tensor-core candidate filter + exact fp32 re-check; *overflowed = 1 -> results invalid, use the fp32 path
+bool cir_stage1_topk_tc_supported(const cir_ctx* ctx, int64_t Q, int64_t G, int64_t K);
+size_t cir_stage1_topk_tc_workspace_bytes(int64_t Q, int64_t G, int64_t K);
+int cir_stage1_topk_tc(cir_ctx* ctx, const float* q_emb, const float* g_emb, int64_t Q, int64_t G, const int32_t* exclude, int64_t col_offset,
+                       int64_t K, float* top_dist, int32_t* top_idx, void* workspace, size_t workspace_bytes, int* overflowed);
 // true when cir_gemm_tcgen05 would use the cta_group::2 pair tile for this shape (the fused LayerNorm needs it)
 bool cir_gemm_uses_pair(const cir_ctx* ctx, int64_t M, int64_t N, int batch);    // attention_tc.cu; CIR_EUNSUPPORTED -> caller falls back

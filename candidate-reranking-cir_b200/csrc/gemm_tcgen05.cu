@@ -55,6 +55,10 @@ struct Params {
   const float* ln_gamma; const float* ln_beta; float ln_eps; int32_t ln_fuse;
   // virtual LayerNorm (cir_gemm_ln): see include/cir_b200.h
   cir_gemm_ln vl;
+  // threshold filter (FILT kernels, stage-I similarity tiles): nothing is stored; every accumulator >= thr[row] is appended
+  // to the row's candidate list as (global column, value bits)
+  cir_gemm_filter flt;
+  int32_t n_major;         // 1: tiles ordered n-block major (all m-blocks of a W block side by side: W streams from HBM once)
 };
 
 // tile sequence of one worker: plain round-robin over tiles, or (LayerNorm fusion) round-robin over m-blocks with the
@@ -73,6 +77,11 @@ __device__ __forceinline__ bool next_tile(const Params& p, int worker, int num_w
   const int tiles_per_batch = p.m_blocks * p.n_blocks;
   b = tile / tiles_per_batch;
   const int r = tile - b * tiles_per_batch;
+  if (p.n_major) {
+    n_blk = r / p.m_blocks;
+    m_blk = r - n_blk * p.m_blocks;
+    return true;
+  }
   m_blk = r / p.n_blocks;
   n_blk = r - m_blk * p.n_blocks;
   return true;
@@ -91,7 +100,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 // ----------------------------------------------------------------------------- the kernel
-template <int BN, bool PAIR, bool LN, bool VL>
+template <int BN, bool PAIR, bool LN, bool VL, bool FILT>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_c, const Params p) {
@@ -230,6 +239,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int64_t row = row_base + lane;
       const bool row_ok = row < p.M;
       const int64_t ntile0 = (int64_t)n_blk * BN;
+      float flt_thr = INFINITY;
+      if constexpr (FILT) { if (row_ok) flt_thr = __ldg(p.flt.thr + row); }
       if (etid < BN) {
         const int64_t n = ntile0 + etid;
         sbias[acc * BN + etid] = (p.bias && n < p.N) ? __ldg(p.bias + b * p.bias_bstride + n) : 0.f;
@@ -292,6 +303,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tmem_ld_32x32b_x32(taddr + 32, v1);
         tmem_ld_wait();
         if (n00 >= p.N) continue;                          // whole span beyond N (warp-uniform)
+        if constexpr (FILT) {
+          // 64 similarities of this thread's row: one max tree, and only a span that holds a candidate is looked at again
+          float mx = __uint_as_float(v0[0]);
+#pragma unroll
+          for (int j = 1; j < 32; j++) mx = fmaxf(mx, __uint_as_float(v0[j]));
+#pragma unroll
+          for (int j = 0; j < 32; j++) mx = fmaxf(mx, __uint_as_float(v1[j]));
+          if (mx >= flt_thr) {
+#pragma unroll
+            for (int j = 0; j < 64; j++) {
+              const float sv = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
+              if (sv >= flt_thr && n00 + j < p.N) {
+                const int slot = atomicAdd(p.flt.count + row, 1);
+                if (slot < p.flt.cap) p.flt.cand[row * p.flt.cap + slot] = make_uint2((uint32_t)(p.flt.col_base + n00 + j), __float_as_uint(sv));
+                else *p.flt.overflow = 1;
+              }
+            }
+          }
+          continue;
+        }
         float f[64];
         if (VL && p.vl.a_stats) {                           // LN(A) W^T = rstd (A W'^T) - rstd mu colsum + bias'
           const float4* sb = reinterpret_cast<const float4*>(sbias + acc * BN + col0);
@@ -614,12 +645,13 @@ static int make_map_c(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t 
   return cir_make_map_3d(ctx, map, base, N, M, batch, ldc, c_bstride, 64, 32, 1);
 }
 
-template <int BN, bool PAIR, bool LN, bool VL = false>
+template <int BN, bool PAIR, bool LN, bool VL = false, bool FILT = false>
 static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc) {
   using C = tc::Cfg<BN, PAIR>;
-  const unsigned bit = 1u << (8 + (BN == 128 ? 0 : 1) + (PAIR ? 2 : 0) + (LN ? 4 : 0) + (VL ? 8 : 0));   // per context: the attribute is per device
+  const unsigned bit = FILT ? 1u << (26 + (BN == 128 ? 0 : 1) + (PAIR ? 1 : 0))
+                            : 1u << (8 + (BN == 128 ? 0 : 1) + (PAIR ? 2 : 0) + (LN ? 4 : 0) + (VL ? 8 : 0));   // per context: the attribute is per device
   if (!(ctx->func_attr_mask & bit)) {
-    CIR_CUDA(cudaFuncSetAttribute(tc::gemm_tcgen05_kernel<BN, PAIR, LN, VL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES + (VL ? C::VL_BYTES : 0)));
+    CIR_CUDA(cudaFuncSetAttribute(tc::gemm_tcgen05_kernel<BN, PAIR, LN, VL, FILT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES + (VL ? C::VL_BYTES : 0)));
     ctx->func_attr_mask |= bit;
   }
   const int slots = PAIR ? ctx->num_sms / 2 : ctx->num_sms;
@@ -637,7 +669,7 @@ static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, c
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cir_prof_gemm_begin(ctx, 2.0 * (double)p.M * (double)p.N * (double)p.K * (double)p.batch);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_tcgen05_kernel<BN, PAIR, LN, VL>, ma, mw, mc, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_tcgen05_kernel<BN, PAIR, LN, VL, FILT>, ma, mw, mc, p);
   cir_prof_gemm_end(ctx);
   if (e != cudaSuccess) { cir_set_error("tcgen05 GEMM launch failed: %s", cudaGetErrorString(e)); return CIR_ECUDA; }
   CIR_LAUNCH_CHECK(ctx);
@@ -708,4 +740,29 @@ int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a) {
   if (use_pair) return p.ln_fuse ? launch_tc<256, true, true>(ctx, p, ma, mw, mc) : launch_tc<256, true, false>(ctx, p, ma, mw, mc);
   if (use128) return launch_tc<128, false, false>(ctx, p, ma, mw, mc);
   return launch_tc<256, false, false>(ctx, p, ma, mw, mc);
+}
+
+// Similarity tiles with a threshold filter instead of an output matrix (stage-I top-K): S = A W^T is computed tile by tile on the
+// tensor cores (bf16 operands, fp32 accumulation) and never stored; see cir_gemm_filter in common.cuh.
+int cir_gemm_tcgen05_filter(cir_ctx* ctx, const void* A, const void* W, int64_t M, int64_t N, int64_t K, const cir_gemm_filter* f) {
+  if (M == 0 || N == 0) return CIR_OK;
+  CIR_CHECK_ARG(ctx->dtype == CIR_DTYPE_BF16 && K % 64 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "gemm_filter: bf16 context, K % 64 == 0, aligned operands");
+  CIR_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && f && f->thr && f->count && f->cand && f->overflow && f->cap > 0, "gemm_filter: bad argument");
+  tc::Params p{};
+  p.M = M; p.N = N; p.K = K; p.batch = 1;
+  p.flt = *f;
+  p.n_major = 1;
+  const int64_t pair_tiles = ((M + 2 * tc::BM - 1) / (2 * tc::BM)) * ((N + 255) / 256);
+  const bool use_pair = ctx->gemm_pair && pair_tiles >= ctx->num_sms / 2;
+  const int tile_m = use_pair ? 2 * tc::BM : tc::BM;
+  p.m_blocks = (int32_t)((M + tile_m - 1) / tile_m);
+  p.n_blocks = (int32_t)((N + 255) / 256);
+  p.k_blocks = (int32_t)(K / tc::BK);
+  const int64_t nt = (int64_t)p.m_blocks * p.n_blocks;
+  CIR_CHECK_ARG(nt < (1ll << 31), "gemm_filter: too many tiles");
+  p.num_tiles = (int32_t)nt;
+  CUtensorMap ma, mw;
+  CIR_TRY(cir_make_map_2d(ctx, &ma, A, M, K, K, tc::BM));
+  CIR_TRY(cir_make_map_2d(ctx, &mw, W, N, K, K, use_pair ? 128 : 256));
+  return use_pair ? launch_tc<256, true, false, false, true>(ctx, p, ma, mw, ma) : launch_tc<256, false, false, false, true>(ctx, p, ma, mw, ma);
 }

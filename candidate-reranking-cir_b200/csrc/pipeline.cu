@@ -76,6 +76,7 @@ extern "C" int cir_create(cir_ctx** out, int device, int dtype) {
   c->prune_last = 1;
   c->dedup_first = 1;
   c->fuse_qkv = 1;
+  c->stage1_tc = 1;
   c->gemm_tma_store = 1;
   c->func_attr_mask = 0;
   c->virtual_ln = 0;
@@ -139,6 +140,7 @@ extern "C" int cir_set_attention_impl(cir_ctx* ctx, int impl) {
 extern "C" int cir_set_prune_last_layer(cir_ctx* ctx, int enable) { ctx->prune_last = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_set_dedup_first_layer(cir_ctx* ctx, int enable) { ctx->dedup_first = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_set_fuse_qkv_attention(cir_ctx* ctx, int enable) { ctx->fuse_qkv = enable ? 1 : 0; return CIR_OK; }
+extern "C" int cir_set_stage1_tensor_cores(cir_ctx* ctx, int enable) { ctx->stage1_tc = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_set_fuse_layernorm(cir_ctx* ctx, int enable) { ctx->fuse_ln = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_set_virtual_layernorm(cir_ctx* ctx, int enable) { ctx->virtual_ln = enable; return CIR_OK; }   // 1 both, 2 self-LN only, 3 FFN-LN only
 extern "C" int cir_set_gemm_tma_store(cir_ctx* ctx, int enable) { ctx->gemm_tma_store = enable ? 1 : 0; return CIR_OK; }

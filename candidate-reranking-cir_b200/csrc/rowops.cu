@@ -69,24 +69,91 @@ __device__ __forceinline__ void layernorm24(float (&v)[PER_LANE], const float* g
   for (int i = 0; i < PER_LANE; i++) v[i] = fmaf((v[i] - mean) * rstd, g[i], b[i]);
 }
 
+// The raw 24 elements of one row held by this lane, loaded now and unpacked later (so that the next row's loads are in
+// flight while the current row is reduced).
+template <typename T> struct RawRow;
+template <> struct RawRow<bf16> {
+  uint4 q[3];
+  __device__ __forceinline__ void load(const bf16* row, int lane) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) q[i] = *reinterpret_cast<const uint4*>(row + (lane + 32 * i) * 8);
+  }
+  __device__ __forceinline__ void unpack(float (&v)[PER_LANE]) const {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q[i]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) { float2 f = __bfloat1622float2(h[k]); v[8 * i + 2 * k] = f.x; v[8 * i + 2 * k + 1] = f.y; }
+    }
+  }
+};
+template <> struct RawRow<float> {
+  float4 q[6];
+  __device__ __forceinline__ void load(const float* row, int lane) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float4* p = reinterpret_cast<const float4*>(row + (lane + 32 * i) * 8);
+      q[2 * i] = p[0]; q[2 * i + 1] = p[1];
+    }
+  }
+  __device__ __forceinline__ void unpack(float (&v)[PER_LANE]) const {
+#pragma unroll
+    for (int i = 0; i < 6; i++) { v[4 * i] = q[i].x; v[4 * i + 1] = q[i].y; v[4 * i + 2] = q[i].z; v[4 * i + 3] = q[i].w; }
+  }
+};
+
+// y[r] = LayerNorm(x[r % x_rows] + res[r]) * gamma[g] + beta[g].  One warp walks LN_ROWS consecutive rows: gamma / beta stay
+// in registers (they change only at a group edge), and the loads of row i+1 are issued before row i is reduced, so a warp
+// always has a row of HBM reads in flight.  The single-row-per-warp version re-read gamma/beta through L1 for every row
+// (twice the payload bytes) and measured 4.3 TB/s; the arithmetic (operation order) is unchanged.
+constexpr int LN_ROWS = 4;
 template <typename TX, typename TR, typename TY>
 __global__ void __launch_bounds__(WARPS * 32)
 add_layernorm_kernel(const TX* __restrict__ x, int64_t x_rows, const TR* __restrict__ res, const float* __restrict__ gamma,
                      const float* __restrict__ beta, int64_t rows_per_group, TY* __restrict__ y, int64_t rows, float eps) {
   const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (r >= rows) return;
-  float v[PER_LANE];
-  load_row<TX>(x + (r % x_rows) * D, lane, v);
-  if (res) {
-    float t[PER_LANE];
-    load_row<TR>(res + r * D, lane, t);
+  const int64_t r0 = ((int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5)) * LN_ROWS;
+  if (r0 >= rows) return;
+  const int n = (int)(rows - r0 < LN_ROWS ? rows - r0 : LN_ROWS);
+  RawRow<TX> xr;
+  RawRow<TR> rr;
+  xr.load(x + (r0 % x_rows) * D, lane);
+  if (res) rr.load(res + r0 * D, lane);
+  float g[PER_LANE], b[PER_LANE];
+  int64_t grp = -1;
+#pragma unroll 1
+  for (int i = 0; i < n; i++) {
+    const int64_t r = r0 + i;
+    float v[PER_LANE];
+    xr.unpack(v);
+    if (res) {
+      float t[PER_LANE];
+      rr.unpack(t);
 #pragma unroll
-    for (int i = 0; i < PER_LANE; i++) v[i] += t[i];
+      for (int k = 0; k < PER_LANE; k++) v[k] += t[k];
+    }
+    if (i + 1 < n) {                                          // next row's reads go out before this row's reductions
+      xr.load(x + ((r + 1) % x_rows) * D, lane);
+      if (res) rr.load(res + (r + 1) * D, lane);
+    }
+    const int64_t gr = r / rows_per_group;
+    if (gr != grp) {                                          // warp-uniform
+      grp = gr;
+      load_row<float>(gamma + gr * D, lane, g);
+      load_row<float>(beta + gr * D, lane, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < PER_LANE; k++) s += v[k];
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < PER_LANE; k++) { float d = v[k] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+    for (int k = 0; k < PER_LANE; k++) v[k] = fmaf((v[k] - mean) * rstd, g[k], b[k]);
+    store_row<TY>(y + r * D, lane, v);
   }
-  const int64_t g = r / rows_per_group;
-  layernorm24(v, gamma + g * D, beta + g * D, eps, lane);
-  store_row<TY>(y + r * D, lane, v);
 }
 
 // y[r] = LN2( m[r % m_rows] + LN1(raw[r]) ): LN1's statistics come as partial (sum, sum of squares) pairs written by the
@@ -237,7 +304,7 @@ extern "C" int cir_add_layernorm(cir_ctx* ctx, const void* x, int x_f32, int64_t
   if (rows == 0) return CIR_OK;
   CIR_CHECK_ARG(x && gamma && beta && y && x_rows > 0 && rows_per_group > 0, "add_layernorm: null/zero argument");
   const bool f32 = ctx->dtype == CIR_DTYPE_F32;
-  dim3 grid(row_blocks(rows)), block(WARPS * 32);
+  dim3 grid(row_blocks((rows + LN_ROWS - 1) / LN_ROWS)), block(WARPS * 32);
   {
     const double es = f32 ? 4.0 : 2.0;
     cir_prof_begin(ctx, CIR_PROF_LAYERNORM, (double)rows * D * ((x_f32 ? 4.0 : es) + (res ? es : 0.0) + (y_f32 ? 4.0 : es)));

@@ -213,9 +213,15 @@ extern "C" int cir_topk_from_dist(cir_ctx* ctx, const float* dist, int64_t Q, in
 
 static const int64_t kSimChunk = 8192;    // gallery columns per similarity tile
 
-extern "C" size_t cir_stage1_topk_workspace_bytes(int64_t Q, int64_t G, int64_t K) {
+static size_t stage1_fp32_workspace_bytes(int64_t Q, int64_t G, int64_t K) {
   const int64_t gc = G < kSimChunk ? G : kSimChunk;
   return cir_topk_workspace_bytes(Q, G, K) + align_up((size_t)Q * (size_t)gc * sizeof(float), 256);
+}
+extern "C" size_t cir_stage1_topk_workspace_bytes(int64_t Q, int64_t G, int64_t K) {
+  // the tensor-core path (large galleries, bf16 contexts) and the fp32 path use the same buffer one after the other
+  const size_t a = stage1_fp32_workspace_bytes(Q, G, K);
+  const size_t b = (G >= 16384 && K >= 1 && K <= MAXK) ? cir_stage1_topk_tc_workspace_bytes(Q, G, K) : 0;
+  return a > b ? a : b;
 }
 
 extern "C" int cir_stage1_topk(cir_ctx* ctx, const float* q_emb, const float* g_emb, int64_t Q, int64_t G,
@@ -225,6 +231,13 @@ extern "C" int cir_stage1_topk(cir_ctx* ctx, const float* q_emb, const float* g_
   if (Q == 0) return CIR_OK;
   CIR_CHECK_ARG(K >= 1 && K <= MAXK, "stage1_topk: K=%lld out of range [1,%d]", (long long)K, MAXK);
   if (workspace_bytes < cir_stage1_topk_workspace_bytes(Q, G, K)) { cir_set_error("stage1_topk: workspace too small"); return CIR_EWORKSPACE; }
+  if (cir_stage1_topk_tc_supported(ctx, Q, G, K)) {
+    // large gallery: candidate filter on the tensor cores + exact fp32 re-check (bit-identical results); an overflowing
+    // candidate list (adversarial gallery order / thousands of near-duplicates) falls through to the fp32 path below
+    int overflowed = 0;
+    CIR_TRY(cir_stage1_topk_tc(ctx, q_emb, g_emb, Q, G, exclude, col_offset, K, top_dist, top_idx, workspace, workspace_bytes, &overflowed));
+    if (!overflowed) return CIR_OK;
+  }
   uint64_t* best = (uint64_t*)workspace;
   float* sim = (float*)((char*)workspace + cir_topk_workspace_bytes(Q, G, K));
   const int64_t gc = G < kSimChunk ? G : kSimChunk;

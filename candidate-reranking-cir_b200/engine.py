@@ -72,6 +72,10 @@ class Engine:
         """bf16, L = 16 / 32: QKV projection + masked text self-attention as one kernel (default on; bit-equal to the unfused path)."""
         N.check(self._lib.cir_set_fuse_qkv_attention(self.ctx, 1 if enable else 0))
 
+    def set_stage1_tensor_cores(self, enable: bool):
+        """bf16, G >= 16,384: stage-I top-K filters candidates on the tensor cores and re-checks them in fp32 (default on; bit-equal)."""
+        N.check(self._lib.cir_set_stage1_tensor_cores(self.ctx, 1 if enable else 0))
+
     def set_virtual_layernorm(self, enable: bool):
         """stage II: never materialise the self-attention / FFN LayerNorms (cir_gemm_ln); bf16 only."""
         N.check(self._lib.cir_set_virtual_layernorm(self.ctx, int(enable)))

@@ -97,6 +97,7 @@ _SIGS = {
     "cir_set_prune_last_layer": (C.c_int, [vp, C.c_int]),
     "cir_set_dedup_first_layer": (C.c_int, [vp, C.c_int]),
     "cir_set_fuse_qkv_attention": (C.c_int, [vp, C.c_int]),
+    "cir_set_stage1_tensor_cores": (C.c_int, [vp, C.c_int]),
     "cir_set_fuse_layernorm": (C.c_int, [vp, C.c_int]),
     "cir_set_virtual_layernorm": (C.c_int, [vp, C.c_int]),
     "cir_set_gemm_tma_store": (C.c_int, [vp, C.c_int]),

@@ -152,6 +152,18 @@ def make_images(n: int, image_size: int = 384, seed: int = 1) -> torch.Tensor:
     return torch.randn(n, 3, image_size, image_size, generator=g)
 
 
+def make_diverse_images(n: int, image_size: int = 384, seed: int = 1) -> torch.Tensor:
+    """``make_images`` with a per-image contrast (log-uniform in [0.15, 6]) and brightness offset (uniform in [-3, 3]):
+    a random-init ViT maps i.i.d. noise images to nearly identical token sets, so without this the candidates of a query are
+    indistinguishable to the stage-II scorer (score spread below bf16 rounding noise)."""
+    import math
+    img = make_images(n, image_size, seed)
+    g = torch.Generator().manual_seed(seed + 7700)
+    c = torch.exp(torch.linspace(math.log(0.15), math.log(6.0), n))[torch.randperm(n, generator=g)]
+    m = torch.linspace(-3.0, 3.0, n)[torch.randperm(n, generator=g)]
+    return img * c[:, None, None, None] + m[:, None, None, None]
+
+
 def make_token_ids(n: int, length: int = 32, seed: int = 2, min_len: int | None = None):
     """Token ids/mask shaped like BertTokenizer output: [CLS] w.. [SEP] [PAD]..; the
     caller overwrites ids[:,0] with ENC_TOKEN_ID as the reference does

@@ -74,6 +74,10 @@ int  cir_set_dedup_first_layer(cir_ctx* ctx, int enable);
 /* bf16 mode, captions of 16 or 32 tokens: the query/key/value Linears and the masked text self-attention run as ONE kernel
  * (cir_qkv_attention) -- the [rows, 2304] projection never reaches HBM.  Default on; 0 = GEMM + attention kernel (bit-equal). */
 int  cir_set_fuse_qkv_attention(cir_ctx* ctx, int enable);
+/* bf16 contexts, galleries of >= 16,384 rows: cir_stage1_topk computes the similarities on the tensor cores (bf16 operands) only to
+ * FILTER candidates with a rigorous error margin, then re-computes the survivors in fp32 -- results are bit-identical to the
+ * fp32 path.  Default on; 0 = fp32 CUDA-core similarities for every gallery row. */
+int  cir_set_stage1_tensor_cores(cir_ctx* ctx, int enable);
 /* bf16 mode: fuse LayerNorm into the long-K N=768 pair-tile GEMM epilogue (FFN2): statistics in the epilogue, in-place
  * normalisation pass from L2.  Default OFF: measured 53.7k vs 54.4k triplets/s for the separate LayerNorm kernels. */
 int  cir_set_fuse_layernorm(cir_ctx* ctx, int enable);

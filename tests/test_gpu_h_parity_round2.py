@@ -11,7 +11,7 @@ import pytest
 import torch
 
 import cir_b200 as cir
-from helpers import golden_weights, load_golden
+from helpers import golden_images, golden_weights, load_golden
 from oracle import cir_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -25,7 +25,7 @@ def config1():
     sd1, sd2 = golden_weights(g)
     m1 = cir.blip_stage1.blip_stage1(image_size=384, state_dict=sd1, precision="bf16")
     m2 = cir.blip_stage2.blip_stage2(image_size=384, state_dict=sd2, precision="bf16")
-    tokens2 = m2.img_embed(syn.make_images(int(g["G"]), 384, seed=1))        # the stage-II model's ViT (validate_stage2.py:145,293)
+    tokens2 = m2.img_embed(golden_images(g))                                 # the stage-II model's ViT (validate_stage2.py:145,293)
     return g, m1, m2, tokens2
 
 
@@ -85,7 +85,7 @@ def test_config1_fp32_check_mode(config1):
     sd1, sd2 = golden_weights(g)
     m1 = cir.blip_stage1.blip_stage1(image_size=384, state_dict=sd1, precision="fp32")
     m2 = cir.blip_stage2.blip_stage2(image_size=384, state_dict=sd2, precision="fp32")
-    tokens = m2.img_embed(syn.make_images(int(g["G"]), 384, seed=1))
+    tokens = m2.img_embed(golden_images(g))
     assert np.abs(tokens[:, 0, :].cpu().numpy() - g["tokens2_cls"]).max() < 2e-4
     rows = [0, 5]
     ids, mask = torch.tensor(g["ids"][rows]), torch.tensor(g["mask"][rows])

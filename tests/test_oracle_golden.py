@@ -137,8 +137,9 @@ def test_config1_8x50_matches_reference(golden_dir):
     two of the eight queries (the CPU budget of this suite), and the label / recall bookkeeping for all of them."""
     g = _load(golden_dir, "config1_8x50.npz")
     sd1 = syn.make_stage1_state_dict(int(g["seed"]), 384, "reference")
-    sd2 = syn.make_stage2_state_dict(int(g["seed"]), 384, "reference", head_gain=1.0)
-    images = syn.make_images(int(g["G"]), 384, seed=1)
+    sd2 = syn.make_stage2_state_dict(int(g["seed"]), 384, "reference", head_gain=1.0, cross_gain=float(g["cross_gain"]))
+    assert str(g["images"]) == "diverse"
+    images = syn.make_diverse_images(int(g["G"]), 384, seed=1)
     ids, mask = torch.tensor(g["ids"]), torch.tensor(g["mask"])
     with torch.no_grad():
         tokens2 = O.vit_forward(sd2, images)
@@ -153,7 +154,7 @@ def test_config1_8x50_matches_reference(golden_dir):
     assert np.array_equal(O.rerank_order(torch.tensor(g["scores"])).numpy(), g["order"])
     assert O.recall_at(O.sorted_labels(sc, g["k_labels"]), (1, 5, 10, 50)) == g["recalls"].tolist()
     assert g["recalls"].tolist() == [12.5, 37.5, 62.5, 87.5]            # ranks 0 | [1,5) x2 | [5,10) x2 | [10,50) x2 | absent
-    assert float(g["margins"].min()) > 4e-3
+    assert float(g["margins"].min()) > 3e-2          # > 3x the measured bf16 in-row ranking noise (profiles/r02_recall_margin_probe.txt)
 
 
 def test_cirr_stage1_lists_match_reference_writer(golden_dir):
