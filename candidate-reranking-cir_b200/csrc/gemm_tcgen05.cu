@@ -241,7 +241,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int64_t ntile0 = (int64_t)n_blk * BN;
       float flt_thr = INFINITY;
       if constexpr (FILT) { if (row_ok) flt_thr = __ldg(p.flt.thr + row); }
-      if (etid < BN) {
+      if (!FILT && etid < BN) {
         const int64_t n = ntile0 + etid;
         sbias[acc * BN + etid] = (p.bias && n < p.N) ? __ldg(p.bias + b * p.bias_bstride + n) : 0.f;
         if constexpr (VL) {
@@ -265,7 +265,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (p.vl.a_stats && row_ok) row_stats(p.vl.a_stats, p.vl.a_parts, p.vl.a_width, a_scale, a_shift);
         if (p.vl.res_stats && row_ok) row_stats(p.vl.res_stats, p.vl.res_parts, p.vl.res_width, r_scale, r_shift);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");       // epilogue warps only
+      if constexpr (!FILT) asm volatile("bar.sync 1, 256;" ::: "memory");       // epilogue warps only (bias row staged)
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 
@@ -304,23 +304,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tmem_ld_wait();
         if (n00 >= p.N) continue;                          // whole span beyond N (warp-uniform)
         if constexpr (FILT) {
-          // 64 similarities of this thread's row: one max tree, and only a span that holds a candidate is looked at again
-          float mx = __uint_as_float(v0[0]);
+          // 2 x 32 similarities of this thread's row.  Fast path: one max tree per 32 values.  A chunk that holds a candidate
+          // (rare once the thresholds have warmed up) is parked in this lane's 128-byte row of the warp's staging tile so that
+          // the hits can be fetched by (dynamic) bit index; the hit mask is built without branches.
+          auto chunk = [&](const uint32_t (&v)[32], int64_t nbase) {
+            float mx = __uint_as_float(v[0]);
 #pragma unroll
-          for (int j = 1; j < 32; j++) mx = fmaxf(mx, __uint_as_float(v0[j]));
+            for (int j = 1; j < 32; j++) mx = fmaxf(mx, __uint_as_float(v[j]));
+            if (mx >= flt_thr) {
+              uint32_t mask = 0u;
 #pragma unroll
-          for (int j = 0; j < 32; j++) mx = fmaxf(mx, __uint_as_float(v1[j]));
-          if (mx >= flt_thr) {
+              for (int j = 0; j < 32; j++) mask |= (__uint_as_float(v[j]) >= flt_thr ? 1u : 0u) << j;
+              const uint32_t mine = stg + (uint32_t)lane * 128;
 #pragma unroll
-            for (int j = 0; j < 64; j++) {
-              const float sv = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
-              if (sv >= flt_thr && n00 + j < p.N) {
-                const int slot = atomicAdd(p.flt.count + row, 1);
-                if (slot < p.flt.cap) p.flt.cand[row * p.flt.cap + slot] = make_uint2((uint32_t)(p.flt.col_base + n00 + j), __float_as_uint(sv));
-                else *p.flt.overflow = 1;
+              for (int j = 0; j < 8; j++) sts128(mine + (uint32_t)((j ^ (lane & 7)) << 4), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+              while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (nbase + j < p.N) {
+                  uint32_t bits;
+                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(bits) : "r"(mine + (uint32_t)((((j >> 2) ^ (lane & 7)) << 4) + (j & 3) * 4)) : "memory");
+                  const int slot = atomicAdd(p.flt.count + row, 1);
+                  if (slot < p.flt.cap) p.flt.cand[row * p.flt.cap + slot] = make_uint2((uint32_t)(p.flt.col_base + nbase + j), bits);
+                  else *p.flt.overflow = 1;
+                }
               }
             }
-          }
+          };
+          chunk(v0, n00);
+          chunk(v1, n00 + 32);
           continue;
         }
         float f[64];

@@ -32,33 +32,48 @@ __device__ __forceinline__ float from_ordered_bits(uint32_t o) {
   return __uint_as_float(u);
 }
 
-// one warp per row: bf16 copy, ||x - bf16(x)||_2 and ||bf16(x)||_2 (fp32, rounded up by the caller's slack);
-// gmax (optional): running maxima {max ||x||, max ||x - bf16(x)||} over all rows as float bits (non-negative floats order like uints)
+// one warp per TB_ROWS consecutive rows (all loads issued before the first reduction): bf16 copy, ||x - bf16(x)||_2 and ||bf16(x)||_2
+// (fp32, rounded up by the caller's slack); gmax (optional): running maxima {max ||x||, max ||x - bf16(x)||} over all rows as float
+// bits (non-negative floats order like uints)
+constexpr int TB_ROWS = 4;
 __global__ void __launch_bounds__(THREADS)
 to_bf16_kernel(const float* __restrict__ x, int64_t rows, bf16* __restrict__ xb, float* __restrict__ row_err, float* __restrict__ row_nrm,
                uint32_t* __restrict__ gmax) {
   const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
-  if (r >= rows) return;
-  const float4* p = reinterpret_cast<const float4*>(x + r * E);
-  float e2 = 0.f, n2 = 0.f, f2 = 0.f;
+  const int64_t r0 = ((int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5)) * TB_ROWS;
+  if (r0 >= rows) return;
+  float4 v[TB_ROWS][2];
 #pragma unroll
-  for (int i = 0; i < 2; i++) {
-    const float4 v = p[lane + 32 * i];
-    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-    const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
-    e2 += (v.x - a.x) * (v.x - a.x) + (v.y - a.y) * (v.y - a.y) + (v.z - b.x) * (v.z - b.x) + (v.w - b.y) * (v.w - b.y);
-    n2 += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
-    f2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    uint2 o;
-    o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(xb + r * E + (lane + 32 * i) * 4) = o;
-  }
-  e2 = warp_sum(e2); n2 = warp_sum(n2); f2 = warp_sum(f2);
-  if (lane == 0) {
+  for (int t = 0; t < TB_ROWS; t++)
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+      v[t][i] = r0 + t < rows ? reinterpret_cast<const float4*>(x + (r0 + t) * E)[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float mx_full = 0.f, mx_err = 0.f;
+#pragma unroll
+  for (int t = 0; t < TB_ROWS; t++) {
+    const int64_t r = r0 + t;
+    if (r >= rows) break;
+    float e2 = 0.f, n2 = 0.f, f2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const float4 w = v[t][i];
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
+      const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+      e2 += (w.x - a.x) * (w.x - a.x) + (w.y - a.y) * (w.y - a.y) + (w.z - b.x) * (w.z - b.x) + (w.w - b.y) * (w.w - b.y);
+      n2 += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+      f2 += w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w;
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(xb + r * E + (lane + 32 * i) * 4) = o;
+    }
+    e2 = warp_sum(e2); n2 = warp_sum(n2); f2 = warp_sum(f2);
     const float err = sqrtf(e2) * 1.0001f, nrm = sqrtf(n2) * 1.0001f, full = sqrtf(f2) * 1.0001f;
-    if (row_err) { row_err[r] = err; row_nrm[r] = nrm; }
-    if (gmax) { atomicMax(gmax, __float_as_uint(full)); atomicMax(gmax + 1, __float_as_uint(err)); }
+    if (lane == 0 && row_err) { row_err[r] = err; row_nrm[r] = nrm; }
+    mx_full = fmaxf(mx_full, full); mx_err = fmaxf(mx_err, err);
+  }
+  if (lane == 0 && gmax) {                                     // the maxima settle after a few rows: look before paying for an atomic
+    if (__float_as_uint(mx_full) > *(volatile uint32_t*)gmax) atomicMax(gmax, __float_as_uint(mx_full));
+    if (__float_as_uint(mx_err) > *(volatile uint32_t*)(gmax + 1)) atomicMax(gmax + 1, __float_as_uint(mx_err));
   }
 }
 
@@ -102,50 +117,74 @@ __device__ void sort_asc(uint64_t* s, int n) {
   __syncthreads();
 }
 
-// One CTA per query, after a super-block: sort the candidates by approximate similarity (descending), move the threshold to the
-// Ksel-th best minus 2 eps_q and keep what is still above it.  Ksel = K (+1 when a reference index is excluded: it may sit in the list).
+// One CTA per query, after a super-block: find the Ksel-th best approximate similarity among the candidates (radix select on the
+// order-preserving bits, 4 passes of 8 bits -- no sort: the list order is irrelevant), move the threshold to it minus 2 eps_q and
+// keep what is still above.  Ksel = K (+1 when a reference index is excluded: it may sit in the list).
 __global__ void __launch_bounds__(THREADS)
 select_kernel(uint2* __restrict__ cand, int32_t* __restrict__ count, float* __restrict__ thr, int64_t cap, int K, const int32_t* __restrict__ exclude,
               const float* __restrict__ q_err, const float* __restrict__ q_nrm, const uint32_t* __restrict__ gmax, int32_t* __restrict__ flags) {
-  extern __shared__ uint64_t skeys[];
-  __shared__ int s_keep;
+  extern __shared__ uint64_t skeys[];                                       // n entries: (ordered similarity bits) << 32 | column
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_need, s_keep;
   const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x;
   int n = count[q];
-  if (n > cap) { if (threadIdx.x == 0) flags[0] = 1; n = (int)cap; }      // overflow: the caller falls back (list content is incomplete)
+  if (n > cap) { if (tid == 0) flags[0] = 1; n = (int)cap; }               // overflow: the caller falls back (list content is incomplete)
   const int Ksel = K + ((exclude && exclude[q] >= 0) ? 1 : 0);
   if (n < Ksel) return;                                                     // fewer than K candidates so far: keep all, threshold stays
-  int m = 32;
-  while (m < n) m <<= 1;
   uint2* row = cand + q * cap;
-  for (int i = threadIdx.x; i < m; i += THREADS) {
-    uint64_t key = 0ull;                                                    // padding sorts last (descending)
-    if (i < n) { const uint2 c = row[i]; key = ((uint64_t)ordered_bits(__uint_as_float(c.y)) << 32) | (uint32_t)(~c.x); }
-    skeys[i] = key;
+  for (int i = tid; i < n; i += THREADS) { const uint2 c = row[i]; skeys[i] = ((uint64_t)ordered_bits(__uint_as_float(c.y)) << 32) | c.x; }
+  if (tid == 0) { s_prefix = 0u; s_need = Ksel; }
+  // after pass p the top 8 (p + 1) bits of the Ksel-th largest key are known
+  for (int pass = 0; pass < 4; pass++) {
+    const int shift = 24 - 8 * pass;
+    hist[tid] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    const int need = s_need;
+    for (int i = tid; i < n; i += THREADS) {
+      const uint32_t k = (uint32_t)(skeys[i] >> 32);
+      if (pass == 0 || (k >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(k >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {                                                         // bins from the top: first bin where the running count reaches `need`
+      int c[8], tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { c[j] = hist[255 - (tid * 8 + j)]; tot += c[j]; }
+      int incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += t; }
+      int run = incl - tot;                                                 // elements in bins above this lane's eight
+      if (run < need && incl >= need) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (run < need && run + c[j] >= need) { s_prefix = prefix | ((uint32_t)(255 - (tid * 8 + j)) << shift); s_need = need - run; }
+          run += c[j];
+        }
+      }
+    }
+    __syncthreads();
   }
-  sort_desc(skeys, m);
-  const float kth = from_ordered_bits((uint32_t)(skeys[Ksel - 1] >> 32));
+  const float kth = from_ordered_bits(s_prefix);
   const float g_nrm = __uint_as_float(gmax[0]), g_err = __uint_as_float(gmax[1]);
   // |q.g - bf16(q).bf16(g)| <= ||q - q^|| ||g|| + ||q^|| ||g - g^||; + fp32 accumulation slack of both the tensor-core sum and the exact chain
   const float eps = (q_err[q] * g_nrm + q_nrm[q] * g_err) * 1.001f + 1e-4f * (q_nrm[q] + q_err[q]) * g_nrm;
   const float t_new = fmaxf(thr[q], kth - 2.0f * eps);
-  if (threadIdx.x == 0) s_keep = 0;
+  if (tid == 0) s_keep = 0;
   __syncthreads();
-  // entries are sorted: the survivors are a prefix
-  int local = 0;
-  for (int i = threadIdx.x; i < n; i += THREADS) local += from_ordered_bits((uint32_t)(skeys[i] >> 32)) >= t_new ? 1 : 0;
-  atomicAdd(&s_keep, local);
-  __syncthreads();
-  const int keep = s_keep;
-  for (int i = threadIdx.x; i < keep; i += THREADS) {
+  for (int i = tid; i < n; i += THREADS) {
     const uint64_t key = skeys[i];
-    row[i] = make_uint2(~(uint32_t)(key & 0xFFFFFFFFu), __float_as_uint(from_ordered_bits((uint32_t)(key >> 32))));
+    const float sv = from_ordered_bits((uint32_t)(key >> 32));
+    if (sv >= t_new) row[atomicAdd(&s_keep, 1)] = make_uint2((uint32_t)(key & 0xFFFFFFFFu), __float_as_uint(sv));
   }
-  if (threadIdx.x == 0) { count[q] = keep; thr[q] = t_new; }
+  __syncthreads();
+  if (tid == 0) { count[q] = s_keep; thr[q] = t_new; }
 }
 
 // One CTA per query: exact fp32 distances of the surviving candidates (fmaf over k = 0..255 in order: sgemm_nt_kernel's sum),
 // composite (distance bits, global index) keys, ascending sort, first K.  Missing entries: index -1, distance +inf (as topk.cu).
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2)
 finalize_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ count, int64_t cap, const float* __restrict__ q_emb,
                 const float* __restrict__ g_emb, const int32_t* __restrict__ exclude, int64_t col_offset, int K,
                 float* __restrict__ out_dist, int32_t* __restrict__ out_idx, int32_t* __restrict__ flags) {
@@ -167,10 +206,16 @@ finalize_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ coun
       const float4* gv = reinterpret_cast<const float4*>(g_emb + (int64_t)gi * E);
       const float4* qv = reinterpret_cast<const float4*>(sq);
       float acc = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < E / 4; k++) {
-        const float4 a = qv[k], b = __ldg(gv + k);
-        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+#pragma unroll 1
+      for (int k0 = 0; k0 < E / 4; k0 += 16) {               // 16 independent 16-byte loads in flight, then the ordered fmaf chain
+        float4 b[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) b[k] = __ldg(gv + k0 + k);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const float4 a = qv[k0 + k];
+          acc = fmaf(a.x, b[k].x, acc); acc = fmaf(a.y, b[k].y, acc); acc = fmaf(a.z, b[k].z, acc); acc = fmaf(a.w, b[k].w, acc);
+        }
       }
       const int64_t global = col_offset + (int64_t)gi;
       if (global != excl) key = ((uint64_t)ordered_bits(1.0f - acc) << 32) | (uint32_t)global;
@@ -224,9 +269,9 @@ int cir_stage1_topk_tc(cir_ctx* ctx, const float* q_emb, const float* g_emb, int
   cudaStream_t st = ctx->stream;
   init_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(w.thr, w.count, Q, w.flags, w.gmax);
   CIR_LAUNCH_CHECK(ctx);
-  to_bf16_kernel<<<(unsigned)((Q + 7) / 8), THREADS, 0, st>>>(q_emb, Q, w.qb, w.q_err, w.q_nrm, nullptr);
+  to_bf16_kernel<<<(unsigned)((Q + 8 * TB_ROWS - 1) / (8 * TB_ROWS)), THREADS, 0, st>>>(q_emb, Q, w.qb, w.q_err, w.q_nrm, nullptr);
   CIR_LAUNCH_CHECK(ctx);
-  to_bf16_kernel<<<(unsigned)((G + 7) / 8), THREADS, 0, st>>>(g_emb, G, w.gb, nullptr, nullptr, w.gmax);
+  to_bf16_kernel<<<(unsigned)((G + 8 * TB_ROWS - 1) / (8 * TB_ROWS)), THREADS, 0, st>>>(g_emb, G, w.gb, nullptr, nullptr, w.gmax);
   CIR_LAUNCH_CHECK(ctx);
   if (!(ctx->func_attr_mask & (1u << 29))) {                  // per context: the attribute is per device
     CIR_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SORT * 8));
