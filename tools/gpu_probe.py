@@ -44,9 +44,9 @@ def stage2_probe(T_per=2048, C=48, L=32, reps=3, configs=((1024, 32), (2048, 48)
     syn = cir.synthetic
     sd2 = syn.make_stage2_state_dict(0, 384, "reference")
     m2 = cir.blip_stage2.blip_stage2(image_size=384, state_dict=sd2, precision="bf16")
-    G = 256
+    G = int(os.environ.get("CIR_PROBE_G", "256"))
     tokens = torch.randn(G, 577, 768, device="cuda").bfloat16()
-    K = 50
+    K = int(os.environ.get("CIR_PROBE_K", "50"))
     ids, mask = syn.make_token_ids(Q, L, seed=2)
     ids[:, 0] = 30523
     z_t = torch.randn(Q, L, 768, device="cuda").bfloat16()
@@ -164,4 +164,4 @@ if __name__ == "__main__":
     if "qkv" in which:
         qkv_probe()
     if "stage2_profile" in which:      # one short pass for an ncu launch list
-        stage2_probe(reps=1, configs=((4096, 64),), Q=96)
+        stage2_probe(reps=1, configs=((4096, 64),), Q=int(os.environ.get("CIR_PROBE_Q", "96")))
