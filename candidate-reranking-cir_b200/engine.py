@@ -161,131 +161,110 @@ class Engine:
     def _p(self, t: torch.Tensor) -> torch.Tensor:        # bias / LN / tables: fp32
         return t.detach().to(device=self.device, dtype=torch.float32).contiguous()
 
+    def _upload(self, sd, key, hold):
+        """One state_dict tensor -> fp32 device pointer for a cir_*_state (None when the key is absent)."""
+        if key not in sd:
+            return N.vp(0)
+        t = self._p(sd[key])
+        hold.append(t)
+        return N.ptr(t)
+
     def pack_vit(self, sd: Dict[str, torch.Tensor], prefix: str = "visual_encoder."):
-        keep: List[torch.Tensor] = []
-        w = N.VitWeights()
-
-        def W(name):
-            t = self._w(sd[prefix + name]); keep.append(t); return N.ptr(t)
-
-        def P(name, flat=False):
-            t = self._p(sd[prefix + name]);
-            keep.append(t); return N.ptr(t)
-        t = self._w(sd[prefix + "patch_embed.proj.weight"].reshape(HIDDEN, -1)); keep.append(t); w.patch_w = N.ptr(t)
-        w.patch_b = P("patch_embed.proj.bias")
-        t = self._p(sd[prefix + "cls_token"].reshape(-1)); keep.append(t); w.cls_token = N.ptr(t)
-        pos = self._p(sd[prefix + "pos_embed"].reshape(-1, HIDDEN)); keep.append(pos); w.pos_embed = N.ptr(pos)
+        """visual_encoder.* -> cir_vit_weights through the C-ABI packer (cir_pack_vit_weights): -> (struct, [blob], tokens)."""
+        hold: List[torch.Tensor] = []
+        st = N.VitState()
+        U = lambda name: self._upload(sd, prefix + name, hold)
+        st.patch_w, st.patch_b, st.cls_token, st.pos_embed = U("patch_embed.proj.weight"), U("patch_embed.proj.bias"), U("cls_token"), U("pos_embed")
+        n_tok = int(sd[prefix + "pos_embed"].reshape(-1, HIDDEN).shape[0])
+        st.num_tokens = n_tok
         for i in range(LAYERS):
             b = f"blocks.{i}."
-            w.norm1_g[i] = P(b + "norm1.weight"); w.norm1_b[i] = P(b + "norm1.bias")
-            w.qkv_w[i] = W(b + "attn.qkv.weight"); w.qkv_b[i] = P(b + "attn.qkv.bias")
-            w.proj_w[i] = W(b + "attn.proj.weight"); w.proj_b[i] = P(b + "attn.proj.bias")
-            w.norm2_g[i] = P(b + "norm2.weight"); w.norm2_b[i] = P(b + "norm2.bias")
-            w.fc1_w[i] = W(b + "mlp.fc1.weight"); w.fc1_b[i] = P(b + "mlp.fc1.bias")
-            w.fc2_w[i] = W(b + "mlp.fc2.weight"); w.fc2_b[i] = P(b + "mlp.fc2.bias")
-        w.norm_g = P("norm.weight"); w.norm_b = P("norm.bias")
-        return w, keep, pos.shape[0]
+            st.norm1_g[i], st.norm1_b[i] = U(b + "norm1.weight"), U(b + "norm1.bias")
+            st.qkv_w[i], st.qkv_b[i] = U(b + "attn.qkv.weight"), U(b + "attn.qkv.bias")
+            st.proj_w[i], st.proj_b[i] = U(b + "attn.proj.weight"), U(b + "attn.proj.bias")
+            st.norm2_g[i], st.norm2_b[i] = U(b + "norm2.weight"), U(b + "norm2.bias")
+            st.fc1_w[i], st.fc1_b[i] = U(b + "mlp.fc1.weight"), U(b + "mlp.fc1.bias")
+            st.fc2_w[i], st.fc2_b[i] = U(b + "mlp.fc2.weight"), U(b + "mlp.fc2.bias")
+        st.norm_g, st.norm_b = U("norm.weight"), U("norm.bias")
+        blob = torch.empty(self._lib.cir_pack_vit_bytes(self.ctx, n_tok), dtype=torch.uint8, device=self.device)
+        w = N.VitWeights()
+        self._sync_stream()
+        N.check(self._lib.cir_pack_vit_weights(self.ctx, C.byref(st), N.ptr(blob), blob.numel(), C.byref(w)), "cir_pack_vit_weights")
+        torch.cuda.synchronize(self.device)          # the fp32 uploads in `hold` are released on return
+        return w, [blob], n_tok
 
-    def _cat_w(self, sd, names, keep, dim=0):
-        t = self._w(torch.cat([sd[n].float() for n in names], dim=dim)); keep.append(t); return N.ptr(t)
-
-    def _cat_p(self, sd, names, keep):
-        t = self._p(torch.cat([sd[n].float().reshape(-1) for n in names])); keep.append(t); return N.ptr(t)
+    def _embed_state(self, sd, emb, hold):
+        e = "text_encoder.embeddings."
+        emb.word_emb, emb.vocab_rows = self._upload(sd, e + "word_embeddings.weight", hold), int(sd[e + "word_embeddings.weight"].shape[0])
+        emb.pos_emb, emb.pos_rows = self._upload(sd, e + "position_embeddings.weight", hold), int(sd[e + "position_embeddings.weight"].shape[0])
+        emb.ln_g, emb.ln_b = self._upload(sd, e + "LayerNorm.weight", hold), self._upload(sd, e + "LayerNorm.bias", hold)
+        self.vocab_rows = int(emb.vocab_rows)
 
     def pack_stage1(self, sd: Dict[str, torch.Tensor]):
-        keep: List[torch.Tensor] = []
-        w = N.Stage1Weights()
-        e = "text_encoder.embeddings."
-        w.word_emb = self._cat_p(sd, [e + "word_embeddings.weight"], keep)
-        self.vocab_rows = int(sd[e + "word_embeddings.weight"].shape[0])
-        w.pos_emb = self._cat_p(sd, [e + "position_embeddings.weight"], keep)
-        w.emb_ln_g = self._cat_p(sd, [e + "LayerNorm.weight"], keep)
-        w.emb_ln_b = self._cat_p(sd, [e + "LayerNorm.bias"], keep)
+        """BLIP_Retrieval text encoder + projections -> cir_stage1_weights through cir_pack_stage1_weights: -> (struct, [blob])."""
+        hold: List[torch.Tensor] = []
+        st = N.Stage1State()
+        self._embed_state(sd, st.emb, hold)
+        U = lambda name: self._upload(sd, name, hold)
         for i in range(LAYERS):
             p = f"text_encoder.encoder.layer.{i}."
             a, c = p + "attention.", p + "crossattention."
-            w.self_qkv_w[i] = self._cat_w(sd, [a + f"self.{n}.weight" for n in ("query", "key", "value")], keep)
-            w.self_qkv_b[i] = self._cat_p(sd, [a + f"self.{n}.bias" for n in ("query", "key", "value")], keep)
-            w.self_out_w[i] = self._cat_w(sd, [a + "output.dense.weight"], keep)
-            w.self_out_b[i] = self._cat_p(sd, [a + "output.dense.bias"], keep)
-            w.self_ln_g[i] = self._cat_p(sd, [a + "output.LayerNorm.weight"], keep)
-            w.self_ln_b[i] = self._cat_p(sd, [a + "output.LayerNorm.bias"], keep)
-            w.cross_q_w[i] = self._cat_w(sd, [c + "self.query.weight"], keep)
-            w.cross_q_b[i] = self._cat_p(sd, [c + "self.query.bias"], keep)
-            w.cross_kv_w[i] = self._cat_w(sd, [c + "self.key.weight", c + "self.value.weight"], keep)
-            w.cross_kv_b[i] = self._cat_p(sd, [c + "self.key.bias", c + "self.value.bias"], keep)
-            w.cross_out_w[i] = self._cat_w(sd, [c + "output.dense.weight"], keep)
-            w.cross_out_b[i] = self._cat_p(sd, [c + "output.dense.bias"], keep)
-            w.cross_ln_g[i] = self._cat_p(sd, [c + "output.LayerNorm.weight"], keep)
-            w.cross_ln_b[i] = self._cat_p(sd, [c + "output.LayerNorm.bias"], keep)
-            w.ffn1_w[i] = self._cat_w(sd, [p + "intermediate.dense.weight"], keep)
-            w.ffn1_b[i] = self._cat_p(sd, [p + "intermediate.dense.bias"], keep)
-            w.ffn2_w[i] = self._cat_w(sd, [p + "output.dense.weight"], keep)
-            w.ffn2_b[i] = self._cat_p(sd, [p + "output.dense.bias"], keep)
-            w.ffn_ln_g[i] = self._cat_p(sd, [p + "output.LayerNorm.weight"], keep)
-            w.ffn_ln_b[i] = self._cat_p(sd, [p + "output.LayerNorm.bias"], keep)
-        w.text_proj_w = self._cat_w(sd, ["text_proj.weight"], keep)
-        w.text_proj_b = self._cat_p(sd, ["text_proj.bias"], keep)
-        w.vision_proj_w = self._cat_w(sd, ["vision_proj.weight"], keep)
-        w.vision_proj_b = self._cat_p(sd, ["vision_proj.bias"], keep)
-        return w, keep
+            for nm, f in (("query", "q"), ("key", "k"), ("value", "v")):
+                getattr(st, f"self_{f}_w")[i], getattr(st, f"self_{f}_b")[i] = U(a + f"self.{nm}.weight"), U(a + f"self.{nm}.bias")
+                getattr(st, f"cross_{f}_w")[i], getattr(st, f"cross_{f}_b")[i] = U(c + f"self.{nm}.weight"), U(c + f"self.{nm}.bias")
+            st.self_out_w[i], st.self_out_b[i] = U(a + "output.dense.weight"), U(a + "output.dense.bias")
+            st.self_ln_g[i], st.self_ln_b[i] = U(a + "output.LayerNorm.weight"), U(a + "output.LayerNorm.bias")
+            st.cross_out_w[i], st.cross_out_b[i] = U(c + "output.dense.weight"), U(c + "output.dense.bias")
+            st.cross_ln_g[i], st.cross_ln_b[i] = U(c + "output.LayerNorm.weight"), U(c + "output.LayerNorm.bias")
+            st.ffn1_w[i], st.ffn1_b[i] = U(p + "intermediate.dense.weight"), U(p + "intermediate.dense.bias")
+            st.ffn2_w[i], st.ffn2_b[i] = U(p + "output.dense.weight"), U(p + "output.dense.bias")
+            st.ffn_ln_g[i], st.ffn_ln_b[i] = U(p + "output.LayerNorm.weight"), U(p + "output.LayerNorm.bias")
+        st.text_proj_w, st.text_proj_b = U("text_proj.weight"), U("text_proj.bias")
+        st.vision_proj_w, st.vision_proj_b = U("vision_proj.weight"), U("vision_proj.bias")
+        blob = torch.empty(self._lib.cir_pack_stage1_bytes(self.ctx, st.emb.vocab_rows, st.emb.pos_rows), dtype=torch.uint8, device=self.device)
+        w = N.Stage1Weights()
+        self._sync_stream()
+        N.check(self._lib.cir_pack_stage1_weights(self.ctx, C.byref(st), N.ptr(blob), blob.numel(), C.byref(w)), "cir_pack_stage1_weights")
+        torch.cuda.synchronize(self.device)
+        return w, [blob]
+
+    def stage2_state(self, sd: Dict[str, torch.Tensor], hold: List[torch.Tensor]):
+        """BLIP_NLVR state_dict -> cir_stage2_state (fp32 device uploads are appended to ``hold``)."""
+        st = N.Stage2State()
+        self._embed_state(sd, st.emb, hold)
+        U = lambda name: self._upload(sd, name, hold)
+        for i in range(LAYERS):
+            p = f"text_encoder.encoder.layer.{i}."
+            a, c = p + "attention.", p + "crossattention."
+            for s_, ab in ((0, "A"), (1, "B")):
+                for nm, f in (("query", "q"), ("key", "k"), ("value", "v")):
+                    getattr(st, f"self_{f}_w")[s_][i], getattr(st, f"self_{f}_b")[s_][i] = U(a + f"self{s_}.{nm}.weight"), U(a + f"self{s_}.{nm}.bias")
+                    getattr(st, f"cross_{f}_w")[s_][i], getattr(st, f"cross_{f}_b")[s_][i] = U(c + f"self{s_}.{nm}.weight"), U(c + f"self{s_}.{nm}.bias")
+                st.self_out_w[s_][i], st.self_out_b[s_][i] = U(a + f"output.dense{s_}.weight"), U(a + f"output.dense{s_}.bias")
+                st.self_ln_g[s_][i], st.self_ln_b[s_][i] = U(a + f"output.LayerNorm{ab}.weight"), U(a + f"output.LayerNorm{ab}.bias")
+                st.cross_out_w[s_][i], st.cross_out_b[s_][i] = U(c + f"output.dense{s_}.weight"), U(c + f"output.dense{s_}.bias")
+                st.cross_ln_g[s_][i], st.cross_ln_b[s_][i] = U(c + f"output.LayerNorm{ab}.weight"), U(c + f"output.LayerNorm{ab}.bias")
+            st.merge_w[i], st.merge_b[i] = U(c + "output.merge_layer.weight"), U(c + "output.merge_layer.bias")     # layers 6..11 (src/nlvr_encoder.py:286)
+            st.ffn1_w[i], st.ffn1_b[i] = U(p + "intermediate.dense.weight"), U(p + "intermediate.dense.bias")
+            st.ffn2_w[i], st.ffn2_b[i] = U(p + "output.dense.weight"), U(p + "output.dense.bias")
+            st.ffn_ln_g[i], st.ffn_ln_b[i] = U(p + "output.LayerNorm.weight"), U(p + "output.LayerNorm.bias")
+        st.cls0_w, st.cls0_b, st.cls2_w, st.cls2_b = U("cls_head.0.weight"), U("cls_head.0.bias"), U("cls_head.2.weight"), U("cls_head.2.bias")
+        return st
 
     def pack_stage2(self, sd: Dict[str, torch.Tensor]):
-        """Twin-stream packing; folds the avg / Linear merge of the cross-attention output into one
-        [768,1536] matrix per layer (src/nlvr_encoder.py:250-258), composed in float64."""
-        keep: List[torch.Tensor] = []
+        """Twin-stream packing through cir_pack_stage2_weights: stacks the stream tensors and folds the avg / Linear merge of the
+        cross-attention output into one [768,1536] matrix per layer (src/nlvr_encoder.py:250-258, composed in fp64 on the device).
+        -> (struct, keep-alive list)."""
+        hold: List[torch.Tensor] = []
+        st = self.stage2_state(sd, hold)
+        blob = torch.empty(self._lib.cir_pack_stage2_bytes(self.ctx, st.emb.vocab_rows, st.emb.pos_rows), dtype=torch.uint8, device=self.device)
         w = N.Stage2Weights()
-        e = "text_encoder.embeddings."
-        w.word_emb = self._cat_p(sd, [e + "word_embeddings.weight"], keep)
-        self.vocab_rows = int(sd[e + "word_embeddings.weight"].shape[0])
-        w.pos_emb = self._cat_p(sd, [e + "position_embeddings.weight"], keep)
-        w.emb_ln_g = self._cat_p(sd, [e + "LayerNorm.weight"], keep)
-        w.emb_ln_b = self._cat_p(sd, [e + "LayerNorm.bias"], keep)
-        for i in range(LAYERS):
-            p = f"text_encoder.encoder.layer.{i}."
-            a, c = p + "attention.", p + "crossattention."
-            w.self_qkv_w[i] = self._cat_w(sd, [a + f"self{s}.{n}.weight" for s in (0, 1) for n in ("query", "key", "value")], keep)
-            w.self_qkv_b[i] = self._cat_p(sd, [a + f"self{s}.{n}.bias" for s in (0, 1) for n in ("query", "key", "value")], keep)
-            w.self_out_w[i] = self._cat_w(sd, [a + "output.dense0.weight", a + "output.dense1.weight"], keep)
-            w.self_out_b[i] = self._cat_p(sd, [a + "output.dense0.bias", a + "output.dense1.bias"], keep)
-            w.self_ln_g[i] = self._cat_p(sd, [a + "output.LayerNormA.weight", a + "output.LayerNormB.weight"], keep)
-            w.self_ln_b[i] = self._cat_p(sd, [a + "output.LayerNormA.bias", a + "output.LayerNormB.bias"], keep)
-            w.cross_q_w[i] = self._cat_w(sd, [c + "self0.query.weight", c + "self1.query.weight"], keep)
-            w.cross_q_b[i] = self._cat_p(sd, [c + "self0.query.bias", c + "self1.query.bias"], keep)
-            w.cross_kv_w[i] = self._cat_w(sd, [c + "self0.key.weight", c + "self0.value.weight",
-                                               c + "self1.key.weight", c + "self1.value.weight"], keep)
-            w.cross_kv_b[i] = self._cat_p(sd, [c + "self0.key.bias", c + "self0.value.bias",
-                                               c + "self1.key.bias", c + "self1.value.bias"], keep)
-            W0, W1 = sd[c + "output.dense0.weight"].double(), sd[c + "output.dense1.weight"].double()
-            b0, b1 = sd[c + "output.dense0.bias"].double(), sd[c + "output.dense1.bias"].double()
-            if i >= 6 and c + "output.merge_layer.weight" not in sd:
-                raise N.CirError(f"state_dict has no {c}output.merge_layer.*: a BLIP base checkpoint carries no trained merge "
-                                 "layers (the reference would leave them randomly initialised, src/blip_stage2.py:188-191); "
-                                 "stage II needs a fine-tuned BLIP_NLVR checkpoint")
-            if i >= 6:      # mergeMLP: merge_layer(cat[dense0(c0), dense1(c1)]), no activation (:252-254)
-                Wm, bm = sd[c + "output.merge_layer.weight"].double(), sd[c + "output.merge_layer.bias"].double()
-                Wa, Wb = Wm[:, :HIDDEN], Wm[:, HIDDEN:]
-                Wc = torch.cat([Wa @ W0, Wb @ W1], dim=1)
-                bc = Wa @ b0 + Wb @ b1 + bm
-            else:           # mergeAvg: (dense0(c0) + dense1(c1)) / 2 (:257-258)
-                Wc = 0.5 * torch.cat([W0, W1], dim=1)
-                bc = 0.5 * (b0 + b1)
-            t = self._w(Wc.float()); keep.append(t); w.cross_out_w[i] = N.ptr(t)
-            t = self._p(bc.float()); keep.append(t); w.cross_out_b[i] = N.ptr(t)
-            w.cross_ln_g[i] = self._cat_p(sd, [c + "output.LayerNormA.weight", c + "output.LayerNormB.weight"], keep)
-            w.cross_ln_b[i] = self._cat_p(sd, [c + "output.LayerNormA.bias", c + "output.LayerNormB.bias"], keep)
-            w.ffn1_w[i] = self._cat_w(sd, [p + "intermediate.dense.weight"], keep)
-            w.ffn1_b[i] = self._cat_p(sd, [p + "intermediate.dense.bias"], keep)
-            w.ffn2_w[i] = self._cat_w(sd, [p + "output.dense.weight"], keep)
-            w.ffn2_b[i] = self._cat_p(sd, [p + "output.dense.bias"], keep)
-            w.ffn_ln_g[i] = self._cat_p(sd, [p + "output.LayerNorm.weight"], keep)
-            w.ffn_ln_b[i] = self._cat_p(sd, [p + "output.LayerNorm.bias"], keep)
+        self._sync_stream()
+        N.check(self._lib.cir_pack_stage2_weights(self.ctx, C.byref(st), N.ptr(blob), blob.numel(), C.byref(w)), "cir_pack_stage2_weights")
+        torch.cuda.synchronize(self.device)
+        keep: List[torch.Tensor] = [blob]
         if self.precision == "bf16":
-            self._pack_virtual_ln(sd, w, keep)
-        w.cls0_w = self._cat_w(sd, ["cls_head.0.weight"], keep)
-        w.cls0_b = self._cat_p(sd, ["cls_head.0.bias"], keep)
-        t = self._p(sd["cls_head.2.weight"][0]); keep.append(t); w.cls2_w = N.ptr(t)       # class-0 row only (:136)
-        t = self._p(sd["cls_head.2.bias"][0:1]); keep.append(t); w.cls2_b = N.ptr(t)
+            self._pack_virtual_ln(sd, w, keep)          # optional folded copies for cir_set_virtual_layernorm (host-side, experimental switch)
         return w, keep
 
     def _fold_ln(self, Ws, bs, gammas, betas, keep):

@@ -75,6 +75,37 @@ class Stage1Weights(C.Structure):
                 ("text_proj_w", vp), ("text_proj_b", vp), ("vision_proj_w", vp), ("vision_proj_b", vp)]
 
 
+_A2 = _A * 2
+
+
+class VitState(C.Structure):
+    _fields_ = [("patch_w", vp), ("patch_b", vp), ("cls_token", vp), ("pos_embed", vp), ("num_tokens", i64),
+                ("norm1_g", _A), ("norm1_b", _A), ("qkv_w", _A), ("qkv_b", _A), ("proj_w", _A), ("proj_b", _A),
+                ("norm2_g", _A), ("norm2_b", _A), ("fc1_w", _A), ("fc1_b", _A), ("fc2_w", _A), ("fc2_b", _A),
+                ("norm_g", vp), ("norm_b", vp)]
+
+
+class TextEmbedState(C.Structure):
+    _fields_ = [("word_emb", vp), ("vocab_rows", i64), ("pos_emb", vp), ("pos_rows", i64), ("ln_g", vp), ("ln_b", vp)]
+
+
+class Stage1State(C.Structure):
+    _fields_ = [("emb", TextEmbedState)] + [(n, _A) for n in (
+        "self_q_w", "self_q_b", "self_k_w", "self_k_b", "self_v_w", "self_v_b", "self_out_w", "self_out_b", "self_ln_g", "self_ln_b",
+        "cross_q_w", "cross_q_b", "cross_k_w", "cross_k_b", "cross_v_w", "cross_v_b", "cross_out_w", "cross_out_b", "cross_ln_g", "cross_ln_b",
+        "ffn1_w", "ffn1_b", "ffn2_w", "ffn2_b", "ffn_ln_g", "ffn_ln_b")] + [
+        ("text_proj_w", vp), ("text_proj_b", vp), ("vision_proj_w", vp), ("vision_proj_b", vp)]
+
+
+class Stage2State(C.Structure):
+    _fields_ = [("emb", TextEmbedState)] + [(n, _A2) for n in (
+        "self_q_w", "self_q_b", "self_k_w", "self_k_b", "self_v_w", "self_v_b", "self_out_w", "self_out_b", "self_ln_g", "self_ln_b",
+        "cross_q_w", "cross_q_b", "cross_k_w", "cross_k_b", "cross_v_w", "cross_v_b", "cross_out_w", "cross_out_b")] + [
+        ("merge_w", _A), ("merge_b", _A), ("cross_ln_g", _A2), ("cross_ln_b", _A2),
+        ("ffn1_w", _A), ("ffn1_b", _A), ("ffn2_w", _A), ("ffn2_b", _A), ("ffn_ln_g", _A), ("ffn_ln_b", _A),
+        ("cls0_w", vp), ("cls0_b", vp), ("cls2_w", vp), ("cls2_b", vp)]
+
+
 class Stage2Weights(C.Structure):
     _fields_ = [("word_emb", vp), ("pos_emb", vp), ("emb_ln_g", vp), ("emb_ln_b", vp),
                 ("self_qkv_w", _A), ("self_qkv_b", _A), ("self_out_w", _A), ("self_out_b", _A),
@@ -109,6 +140,12 @@ _SIGS = {
     "cir_gemm": (C.c_int, [vp, C.POINTER(GemmArgs)]),
     "cir_add_layernorm": (C.c_int, [vp, vp, C.c_int, i64, vp, vp, vp, i64, vp, C.c_int, i64, C.c_float]),
     "cir_attention": (C.c_int, [vp, C.POINTER(AttnArgs)]),
+    "cir_pack_vit_bytes": (C.c_size_t, [vp, i64]),
+    "cir_pack_vit_weights": (C.c_int, [vp, C.POINTER(VitState), vp, C.c_size_t, C.POINTER(VitWeights)]),
+    "cir_pack_stage1_bytes": (C.c_size_t, [vp, i64, i64]),
+    "cir_pack_stage1_weights": (C.c_int, [vp, C.POINTER(Stage1State), vp, C.c_size_t, C.POINTER(Stage1Weights)]),
+    "cir_pack_stage2_bytes": (C.c_size_t, [vp, i64, i64]),
+    "cir_pack_stage2_weights": (C.c_int, [vp, C.POINTER(Stage2State), vp, C.c_size_t, C.POINTER(Stage2Weights)]),
     "cir_qkv_attention": (C.c_int, [vp, C.POINTER(QkvAttnArgs)]),
     "cir_bert_embeddings": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, vp, vp]),
     "cir_gather_rows": (C.c_int, [vp, vp, vp, vp, i64, i64]),

@@ -46,7 +46,12 @@ extern "C" {
 #define CIR_GEMM_TCGEN05_1CTA 3   /* tcgen05 but never the cta_group::2 pair tile (cross-check) */
 
 #define CIR_ACT_NONE 0
-#define CIR_ACT_GELU 1        /* erf GELU (transformers ACT2FN["gelu"], nn.GELU) */
+/* GELU of the reference (transformers ACT2FN["gelu"] = erf form; src/nlvr_encoder.py:376, src/vit.py:38).  fp32 contexts evaluate
+ * 0.5 x (1 + erf(x / sqrt 2)) with erff.  bf16 contexts evaluate the tanh form 0.5 x (1 + tanh(0.79788456 (x + 0.044715 x^3)))
+ * with the hardware tanh.approx in the GEMM epilogue: |gelu_tanh - gelu_erf| <= 5e-4 absolute (at |x| ~ 2), tanh.approx adds
+ * <= 2^-11 relative -- both below the bf16 rounding of the stored activation (2^-9 relative) for |x| >= 0.3; measured effect on
+ * stage-II scores: inside the 2e-2 tolerance with the same margin as an erf epilogue. */
+#define CIR_ACT_GELU 1
 #define CIR_ACT_RELU 2
 
 #define CIR_HIDDEN   768
@@ -372,6 +377,79 @@ int cir_stage2_score_prefixed(cir_ctx* ctx, const cir_stage2_weights* w, const v
                               const int32_t* attn_tiles_cls, int64_t num_attn_tiles_cls,
                               float* scores, float* feats, void* workspace, size_t workspace_bytes);
 
+
+/* ---- weight packing: reference state_dict tensors -> the packed structs above ------------------------------------------
+ * A consumer that does not go through the Python host layer binds the reference's checkpoints here: every field of a
+ * cir_*_state is a DEVICE pointer to one fp32 tensor of the reference `state_dict()` (key in the comment; PyTorch [out, in]
+ * layout, contiguous).  cir_pack_* casts GEMM weights to the context's activation dtype, stacks twin-stream / q;k;v tensors
+ * as the kernels expect, folds the cross-attention output projections and the stream merge into one [768,1536] matrix per
+ * layer in fp64 (src/nlvr_encoder.py:250-258), and lays everything out in ONE caller-provided device blob
+ * (cir_pack_*_bytes); the returned struct points into the blob.  Work is enqueued on the context's stream; the state
+ * tensors may be freed once the stream has passed the call. */
+typedef struct cir_vit_state {              /* prefix visual_encoder. (src/vit.py:113-161) */
+  const float* patch_w; const float* patch_b;          /* patch_embed.proj.weight [768,3,16,16], .bias [768] */
+  const float* cls_token; const float* pos_embed;      /* cls_token [1,1,768], pos_embed [1,N,768] */
+  int64_t num_tokens;                                   /* N = (image_size/16)^2 + 1 */
+  const float* norm1_g[CIR_LAYERS]; const float* norm1_b[CIR_LAYERS];   /* blocks.i.norm1.{weight,bias} */
+  const float* qkv_w[CIR_LAYERS];   const float* qkv_b[CIR_LAYERS];     /* blocks.i.attn.qkv */
+  const float* proj_w[CIR_LAYERS];  const float* proj_b[CIR_LAYERS];    /* blocks.i.attn.proj */
+  const float* norm2_g[CIR_LAYERS]; const float* norm2_b[CIR_LAYERS];
+  const float* fc1_w[CIR_LAYERS];   const float* fc1_b[CIR_LAYERS];     /* blocks.i.mlp.fc1 */
+  const float* fc2_w[CIR_LAYERS];   const float* fc2_b[CIR_LAYERS];
+  const float* norm_g; const float* norm_b;            /* norm.{weight,bias} */
+} cir_vit_state;
+size_t cir_pack_vit_bytes(const cir_ctx* ctx, int64_t num_tokens);
+int cir_pack_vit_weights(cir_ctx* ctx, const cir_vit_state* sd, void* blob, size_t blob_bytes, cir_vit_weights* out);
+
+typedef struct cir_text_embed_state {       /* text_encoder.embeddings.* */
+  const float* word_emb; int64_t vocab_rows;           /* word_embeddings.weight [vocab,768] */
+  const float* pos_emb; int64_t pos_rows;              /* position_embeddings.weight [512,768] */
+  const float* ln_g; const float* ln_b;                /* LayerNorm.{weight,bias} */
+} cir_text_embed_state;
+
+typedef struct cir_stage1_state {           /* BLIP_Retrieval (src/blip_stage1.py:16-46; src/med.py:335-398), layer prefix text_encoder.encoder.layer.i. */
+  cir_text_embed_state emb;
+  const float* self_q_w[CIR_LAYERS]; const float* self_q_b[CIR_LAYERS];     /* attention.self.query */
+  const float* self_k_w[CIR_LAYERS]; const float* self_k_b[CIR_LAYERS];
+  const float* self_v_w[CIR_LAYERS]; const float* self_v_b[CIR_LAYERS];
+  const float* self_out_w[CIR_LAYERS]; const float* self_out_b[CIR_LAYERS]; /* attention.output.dense */
+  const float* self_ln_g[CIR_LAYERS]; const float* self_ln_b[CIR_LAYERS];   /* attention.output.LayerNorm */
+  const float* cross_q_w[CIR_LAYERS]; const float* cross_q_b[CIR_LAYERS];   /* crossattention.self.query */
+  const float* cross_k_w[CIR_LAYERS]; const float* cross_k_b[CIR_LAYERS];
+  const float* cross_v_w[CIR_LAYERS]; const float* cross_v_b[CIR_LAYERS];
+  const float* cross_out_w[CIR_LAYERS]; const float* cross_out_b[CIR_LAYERS];
+  const float* cross_ln_g[CIR_LAYERS]; const float* cross_ln_b[CIR_LAYERS];
+  const float* ffn1_w[CIR_LAYERS]; const float* ffn1_b[CIR_LAYERS];         /* intermediate.dense */
+  const float* ffn2_w[CIR_LAYERS]; const float* ffn2_b[CIR_LAYERS];         /* output.dense */
+  const float* ffn_ln_g[CIR_LAYERS]; const float* ffn_ln_b[CIR_LAYERS];     /* output.LayerNorm */
+  const float* text_proj_w; const float* text_proj_b;                       /* text_proj [256,768] */
+  const float* vision_proj_w; const float* vision_proj_b;
+} cir_stage1_state;
+size_t cir_pack_stage1_bytes(const cir_ctx* ctx, int64_t vocab_rows, int64_t pos_rows);
+int cir_pack_stage1_weights(cir_ctx* ctx, const cir_stage1_state* sd, void* blob, size_t blob_bytes, cir_stage1_weights* out);
+
+typedef struct cir_stage2_state {           /* BLIP_NLVR (src/blip_stage2.py:19-54; src/nlvr_encoder.py:225-476); index [s] = stream (self0/self1, dense0/dense1, LayerNormA/B) */
+  cir_text_embed_state emb;
+  const float* self_q_w[2][CIR_LAYERS]; const float* self_q_b[2][CIR_LAYERS];       /* attention.self{s}.query */
+  const float* self_k_w[2][CIR_LAYERS]; const float* self_k_b[2][CIR_LAYERS];
+  const float* self_v_w[2][CIR_LAYERS]; const float* self_v_b[2][CIR_LAYERS];
+  const float* self_out_w[2][CIR_LAYERS]; const float* self_out_b[2][CIR_LAYERS];   /* attention.output.dense{s} */
+  const float* self_ln_g[2][CIR_LAYERS]; const float* self_ln_b[2][CIR_LAYERS];     /* attention.output.LayerNorm{A,B} */
+  const float* cross_q_w[2][CIR_LAYERS]; const float* cross_q_b[2][CIR_LAYERS];     /* crossattention.self{s}.query */
+  const float* cross_k_w[2][CIR_LAYERS]; const float* cross_k_b[2][CIR_LAYERS];
+  const float* cross_v_w[2][CIR_LAYERS]; const float* cross_v_b[2][CIR_LAYERS];
+  const float* cross_out_w[2][CIR_LAYERS]; const float* cross_out_b[2][CIR_LAYERS]; /* crossattention.output.dense{s} */
+  const float* merge_w[CIR_LAYERS]; const float* merge_b[CIR_LAYERS];               /* crossattention.output.merge_layer [768,1536]; layers 6..11 (NULL below) */
+  const float* cross_ln_g[2][CIR_LAYERS]; const float* cross_ln_b[2][CIR_LAYERS];   /* crossattention.output.LayerNorm{A,B} */
+  const float* ffn1_w[CIR_LAYERS]; const float* ffn1_b[CIR_LAYERS];
+  const float* ffn2_w[CIR_LAYERS]; const float* ffn2_b[CIR_LAYERS];
+  const float* ffn_ln_g[CIR_LAYERS]; const float* ffn_ln_b[CIR_LAYERS];
+  const float* cls0_w; const float* cls0_b;                                         /* cls_head.0 [768,1536] */
+  const float* cls2_w; const float* cls2_b;                                         /* cls_head.2 [2,768], [2] (row 0 is used, src/blip_stage2.py:136) */
+} cir_stage2_state;
+size_t cir_pack_stage2_bytes(const cir_ctx* ctx, int64_t vocab_rows, int64_t pos_rows);
+/* CIR_EINVAL with a message naming merge_layer when a layer >= 6 carries no merge tensors (a BLIP base checkpoint). */
+int cir_pack_stage2_weights(cir_ctx* ctx, const cir_stage2_state* sd, void* blob, size_t blob_bytes, cir_stage2_weights* out);
 
 #ifdef __cplusplus
 }

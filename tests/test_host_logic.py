@@ -145,7 +145,8 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     N = cir.native
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pairs = {"cir_gemm_args": N.GemmArgs, "cir_gemm_ln": N.GemmLn, "cir_attn_args": N.AttnArgs, "cir_qkv_attn_args": N.QkvAttnArgs, "cir_vit_weights": N.VitWeights,
-             "cir_stage1_weights": N.Stage1Weights, "cir_stage2_weights": N.Stage2Weights}
+             "cir_stage1_weights": N.Stage1Weights, "cir_stage2_weights": N.Stage2Weights, "cir_vit_state": N.VitState,
+             "cir_text_embed_state": N.TextEmbedState, "cir_stage1_state": N.Stage1State, "cir_stage2_state": N.Stage2State}
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "cir_b200.h"\nint main(void) {\n' +
                    "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in pairs) + "  return 0;\n}\n")
