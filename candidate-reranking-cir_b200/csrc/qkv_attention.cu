@@ -16,6 +16,7 @@
 // segments.  The arithmetic (operation order included) is that of attention_small_kernel, so fused == unfused bit for bit.
 #include "common.cuh"
 #include "tcgen05_ptx.cuh"
+#include <stdlib.h>
 
 namespace qkvattn {
 using namespace tc;
@@ -51,6 +52,7 @@ struct Params {
   int64_t out_rs, out_bs, bias_bs;
   int64_t a_rows_per_batch, w_rows_per_batch;
   int32_t batch, L, m_blocks, k_blocks, num_tiles;
+  int32_t drain;                        // the MMA thread lets the UMMA queue run empty every `drain` k-blocks (0 = never); see the kernel comment
   float scale;
 };
 
@@ -102,6 +104,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  const uint32_t drain_bar = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + 1);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_gen + STAGES * STAGE_BYTES + STAGING_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES));
   float* sbias = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES);        // [ACC_STAGES][BN]
@@ -114,6 +117,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     tma_prefetch_desc(&map_w);
     for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < ACC_STAGES; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), NUM_EPI_WARPS * 2); }
+    mbar_init(drain_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc_pair<TMEM_COLS>(tmem_ptr_smem);
@@ -153,6 +157,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      uint32_t drain_phase = 0;
       int b_, m_, h_;
       for (int it = 0; next_tile(p, worker, num_workers, it, b_, m_, h_); ++it) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -168,6 +173,15 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             umma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
           umma_commit_pair(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          // The epilogue warps' mma.sync HMMAs share the tensor pipe with this UMMA stream and are only dispatched when the
+          // UMMA queue is empty (ncu: 48 % of their samples were stall_math on the first HMMAs of a burst).  With the ring
+          // full the queue never empties inside a tile, so the attention of tile i would wait for the end of tile i+2's
+          // UMMAs: let the queue run dry once in the middle of every tile (-7 % kernel time).
+          if (p.drain && (kb + 1) % p.drain == 0 && kb + 1 < p.k_blocks) {
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(drain_bar) : "memory");
+            mbar_wait(drain_bar, drain_phase);
+            drain_phase ^= 1;
+          }
         }
         umma_commit_pair(tfull_bar(acc));
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -392,6 +406,7 @@ extern "C" int cir_qkv_attention(cir_ctx* ctx, const cir_qkv_attn_args* a) {
   const int64_t nt = (int64_t)p.m_blocks * HEADS * a->batch;
   CIR_CHECK_ARG(nt < (1ll << 31), "qkv_attention: too many tiles");
   p.num_tiles = (int32_t)nt;
+  { const char* d = getenv("CIR_QKV_DRAIN"); p.drain = d ? atoi(d) : p.k_blocks / 2; }     // measured: 0.812 ms (never) / 0.752 (mid-tile) / 0.767 (every 4) / 0.998 (every k-block)
   CUtensorMap ma, mw;
   CIR_TRY(cir_make_map_2d(ctx, &ma, a->x, a_rows, DM, DM, BM));
   CIR_TRY(cir_make_map_2d(ctx, &mw, a->w, w_rows, DM, DM, SLAB_ROWS));
