@@ -20,13 +20,10 @@ struct cir_ctx {
   int gemm_pair;        // 1 = allow cta_group::2 pair tiles for large GEMMs (default)
   int prune_last;       // 1 = stage II computes the last layer for the CLS rows only (default)
   int gemm_tma_store;   // 1 = bf16 GEMM outputs leave through TMA bulk tensor stores (default)
-  int virtual_ln;       // 1 = stage-II self / FFN LayerNorms are never materialised (cir_gemm_ln), when the weights carry folded copies
   int fuse_qkv;         // 1 = QKV projection + masked text self-attention as one kernel where eligible (default)
   int stage1_tc;        // 1 = stage-I top-K over large galleries filters on the tensor cores, exact fp32 re-check of the survivors (default)
   int dedup_first;      // 1 = stage II runs layer 0's query-only part once per unique query of a chunk (default)
   unsigned func_attr_mask;   // kernels whose dynamic shared-memory limit was raised on this context's device (bit per kernel)
-  int fuse_ln;          // 1 = LayerNorm fused into the N=768 pair-tile GEMM epilogues where eligible (default)
-  const float* ln_gamma; const float* ln_beta; float ln_eps;   // set around ONE cir_gemm call to request the fused LayerNorm
   cudaStream_t stream;
   int num_sms;
   int64_t launches;
@@ -122,8 +119,6 @@ int cir_gemm_tcgen05_filter(cir_ctx* ctx, const void* A, const void* W, int64_t 
 int cir_gemm_simt(cir_ctx* ctx, const cir_gemm_args* a);
 int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a);
 // 2-D bf16 tensor map over a [rows, K] row-major matrix (row stride ld elements), box [box_rows, 64], SWIZZLE_128B
-int cir_ln_cross_virtual(cir_ctx* ctx, const void* raw, const float* stats, int parts, const float* g1, const float* b1, const void* m,
-                         int64_t m_rows, const float* g2, const float* b2, int64_t rows_per_group, void* y, int64_t rows, float eps);
 int cir_make_map_2d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows);
 // 3-D bf16 map, SWIZZLE_128B: dims (d0 contiguous, d1 stride s1, d2 stride s2; strides in elements), box (b0 <= 64, b1, b2)
 int cir_make_map_3d(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1, int64_t s2,
@@ -135,5 +130,3 @@ bool cir_stage1_topk_tc_supported(const cir_ctx* ctx, int64_t Q, int64_t G, int6
 size_t cir_stage1_topk_tc_workspace_bytes(int64_t Q, int64_t G, int64_t K);
 int cir_stage1_topk_tc(cir_ctx* ctx, const float* q_emb, const float* g_emb, int64_t Q, int64_t G, const int32_t* exclude, int64_t col_offset,
                        int64_t K, float* top_dist, int32_t* top_idx, void* workspace, size_t workspace_bytes, int* overflowed);
-// true when cir_gemm_tcgen05 would use the cta_group::2 pair tile for this shape (the fused LayerNorm needs it)
-bool cir_gemm_uses_pair(const cir_ctx* ctx, int64_t M, int64_t N, int batch);    // attention_tc.cu; CIR_EUNSUPPORTED -> caller falls back

@@ -36,8 +36,7 @@ template <int BN, bool PAIR = false> struct Cfg {
   static constexpr int EPI_STAGING = NUM_EPI_WARPS * 4096;   // per-warp 32 x 128 B transpose tiles
   static constexpr int STAGES = (196608 - EPI_STAGING) / STAGE_BYTES;    // 5 (32 KB stages) or 3 (48 KB stages)
   static constexpr int TMEM_COLS = ACC_STAGES * BN;      // 512 / 256
-  static constexpr int VL_BYTES = 3 * ACC_STAGES * BN * 4;   // virtual-LayerNorm variant: column sums, gamma, beta next to the bias rows
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 192 /*barriers*/ + ACC_STAGES * BN * 4 /*bias*/ + EPI_STAGING + 2 * 128 * 2 * 4 /*LayerNorm row statistics*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 192 /*barriers*/ + ACC_STAGES * BN * 4 /*bias*/ + EPI_STAGING;
 };
 
 struct Params {
@@ -49,29 +48,14 @@ struct Params {
   int32_t batch, act, c_f32, res_f32;
   int32_t m_blocks, n_blocks, k_blocks, num_tiles;
   int32_t tma_store;       // 1: bf16 C tiles leave through cp.async.bulk.tensor stores (3-D map: N, M, batch)
-  // fused LayerNorm (pair tiles, N == n_blocks*256 == 768, bf16 C): every worker walks all n-tiles of an
-  // m-block back to back, keeps per-row sum / sum of squares, then normalises its rows IN PLACE (re-reading the
-  // just-written pre-LN values from L2).  gamma/beta: fp32 [batch][N].
-  const float* ln_gamma; const float* ln_beta; float ln_eps; int32_t ln_fuse;
-  // virtual LayerNorm (cir_gemm_ln): see include/cir_b200.h
-  cir_gemm_ln vl;
   // threshold filter (FILT kernels, stage-I similarity tiles): nothing is stored; every accumulator >= thr[row] is appended
   // to the row's candidate list as (global column, value bits)
   cir_gemm_filter flt;
   int32_t n_major;         // 1: tiles ordered n-block major (all m-blocks of a W block side by side: W streams from HBM once)
 };
 
-// tile sequence of one worker: plain round-robin over tiles, or (LayerNorm fusion) round-robin over m-blocks with the
-// n-tiles of a block visited consecutively
+// tile sequence of one worker: plain round-robin over tiles
 __device__ __forceinline__ bool next_tile(const Params& p, int worker, int num_workers, int it, int& b, int& m_blk, int& n_blk) {
-  if (p.ln_fuse) {
-    const int unit = worker + (it / p.n_blocks) * num_workers;
-    if (unit >= p.batch * p.m_blocks) return false;
-    n_blk = it % p.n_blocks;
-    b = unit / p.m_blocks;
-    m_blk = unit - b * p.m_blocks;
-    return true;
-  }
   const int tile = worker + it * num_workers;
   if (tile >= p.num_tiles) return false;
   const int tiles_per_batch = p.m_blocks * p.n_blocks;
@@ -100,7 +84,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 // ----------------------------------------------------------------------------- the kernel
-template <int BN, bool PAIR, bool LN, bool VL, bool FILT>
+template <int BN, bool PAIR, bool FILT>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_c, const Params p) {
@@ -113,7 +97,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + C::STAGES * C::A_BYTES;
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES + C::EPI_STAGING;   // [ring][epilogue staging][barriers][bias][LN stats]
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES + C::EPI_STAGING;   // [ring][epilogue staging][barriers][bias]
   // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
@@ -230,9 +214,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     };
     int acc = 0; uint32_t acc_phase = 0;
     bool tma_store_pending = false;
-    float ln_sum = 0.f, ln_sq = 0.f;                       // fused LayerNorm: this thread's row, this warp's column half
-    float* sstat = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::EPI_STAGING + 192 + ACC_STAGES * BN * 4);   // [2 halves][128 rows][2]
-    float* svl = sstat + 2 * 128 * 2;                      // VL: [3][ACC_STAGES][BN] column sums | gamma | beta
     int b, m_blk, n_blk;
     for (int it = 0; next_tile(p, worker, num_workers, it, b, m_blk, n_blk); ++it) {
       const int64_t row_base = (int64_t)m_blk * TILE_M + rank * BM + quarter * 32;
@@ -244,26 +225,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (!FILT && etid < BN) {
         const int64_t n = ntile0 + etid;
         sbias[acc * BN + etid] = (p.bias && n < p.N) ? __ldg(p.bias + b * p.bias_bstride + n) : 0.f;
-        if constexpr (VL) {
-          svl[acc * BN + etid] = (p.vl.a_stats && n < p.N) ? __ldg(p.vl.a_colsum + b * p.vl.colsum_bstride + n) : 0.f;
-          svl[(ACC_STAGES + acc) * BN + etid] = (p.vl.res_stats && n < p.N) ? __ldg(p.vl.res_gamma + b * p.vl.gb_bstride + n) : 0.f;
-          svl[(2 * ACC_STAGES + acc) * BN + etid] = (p.vl.res_stats && n < p.N) ? __ldg(p.vl.res_beta + b * p.vl.gb_bstride + n) : 0.f;
-        }
-      }
-      // virtual LayerNorm: this thread's row statistics of A (a_scale, a_shift) and of the residual (r_scale, r_shift)
-      float a_scale = 1.f, a_shift = 0.f, r_scale = 1.f, r_shift = 0.f, vs_sum = 0.f, vs_sq = 0.f;
-      if constexpr (VL) {
-        auto row_stats = [&](const float* st, int parts, int width, float& scale, float& shift) {
-          const float2* sp = reinterpret_cast<const float2*>(st) + ((int64_t)b * p.M + row) * parts;
-          float s1 = 0.f, s2 = 0.f;
-          for (int i = 0; i < parts; i++) { const float2 t = __ldg(sp + i); s1 += t.x; s2 += t.y; }
-          const float mu = s1 / (float)width;
-          const float var = fmaxf(s2 / (float)width - mu * mu, 0.f);
-          scale = rsqrtf(var + p.vl.eps);
-          shift = -mu * scale;
-        };
-        if (p.vl.a_stats && row_ok) row_stats(p.vl.a_stats, p.vl.a_parts, p.vl.a_width, a_scale, a_shift);
-        if (p.vl.res_stats && row_ok) row_stats(p.vl.res_stats, p.vl.res_parts, p.vl.res_width, r_scale, r_shift);
       }
       if constexpr (!FILT) asm volatile("bar.sync 1, 256;" ::: "memory");       // epilogue warps only (bias row staged)
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -336,22 +297,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           continue;
         }
         float f[64];
-        if (VL && p.vl.a_stats) {                           // LN(A) W^T = rstd (A W'^T) - rstd mu colsum + bias'
-          const float4* sb = reinterpret_cast<const float4*>(sbias + acc * BN + col0);
-          const float4* sc = reinterpret_cast<const float4*>(svl + acc * BN + col0);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b0 = sb[j >> 2], b1 = sb[8 + (j >> 2)], c0 = sc[j >> 2], c1 = sc[8 + (j >> 2)];
-            f[j] = fmaf(__uint_as_float(v0[j]), a_scale, fmaf(a_shift, c0.x, b0.x));
-            f[j + 1] = fmaf(__uint_as_float(v0[j + 1]), a_scale, fmaf(a_shift, c0.y, b0.y));
-            f[j + 2] = fmaf(__uint_as_float(v0[j + 2]), a_scale, fmaf(a_shift, c0.z, b0.z));
-            f[j + 3] = fmaf(__uint_as_float(v0[j + 3]), a_scale, fmaf(a_shift, c0.w, b0.w));
-            f[32 + j] = fmaf(__uint_as_float(v1[j]), a_scale, fmaf(a_shift, c1.x, b1.x));
-            f[32 + j + 1] = fmaf(__uint_as_float(v1[j + 1]), a_scale, fmaf(a_shift, c1.y, b1.y));
-            f[32 + j + 2] = fmaf(__uint_as_float(v1[j + 2]), a_scale, fmaf(a_shift, c1.z, b1.z));
-            f[32 + j + 3] = fmaf(__uint_as_float(v1[j + 3]), a_scale, fmaf(a_shift, c1.w, b1.w));
-          }
-        } else {
+        {
           const float4* sb = reinterpret_cast<const float4*>(sbias + acc * BN + col0);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -384,24 +330,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               const uint4 rv = lds128(stg + (uint32_t)lane * 128 + (uint32_t)((j ^ (lane & 7)) << 4));
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-              if (VL && p.vl.res_stats) {                    // residual = LN(raw): (t - mu) rstd gamma + beta
-                const float4* sg = reinterpret_cast<const float4*>(svl + (ACC_STAGES + acc) * BN + col0 + j * 8);
-                const float4* sbt = reinterpret_cast<const float4*>(svl + (2 * ACC_STAGES + acc) * BN + col0 + j * 8);
-                const float4 g0 = sg[0], g1 = sg[1], e0 = sbt[0], e1 = sbt[1];
-                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-                const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                  const float2 t = __bfloat1622float2(h2[q]);
-                  f[j * 8 + 2 * q] += fmaf(fmaf(t.x, r_scale, r_shift), gg[2 * q], ee[2 * q]);
-                  f[j * 8 + 2 * q + 1] += fmaf(fmaf(t.y, r_scale, r_shift), gg[2 * q + 1], ee[2 * q + 1]);
-                }
-              } else {
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                  const float2 t = __bfloat1622float2(h2[q]);
-                  f[j * 8 + 2 * q] += t.x; f[j * 8 + 2 * q + 1] += t.y;
-                }
+              for (int q = 0; q < 4; q++) {
+                const float2 t = __bfloat1622float2(h2[q]);
+                f[j * 8 + 2 * q] += t.x; f[j * 8 + 2 * q + 1] += t.y;
               }
             }
             __syncwarp();
@@ -441,25 +372,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
             for (int q = 0; q < 4; q++) h2[q] = __floats2bfloat162_rn(f[j * 8 + 2 * q], f[j * 8 + 2 * q + 1]);
-            if (VL && p.vl.out_stats) {                      // partial row statistics of the ROUNDED values a consumer will read
-#pragma unroll
-              for (int q = 0; q < 4; q++) {
-                const float2 t = __bfloat1622float2(h2[q]);
-                vs_sum += t.x + t.y;
-                vs_sq = fmaf(t.x, t.x, fmaf(t.y, t.y, vs_sq));
-              }
-            }
-            if constexpr (LN) {                             // statistics of the ROUNDED values the in-place pass will read back
-#pragma unroll
-              for (int q = 0; q < 4; q++) {
-                const float2 t = __bfloat1622float2(h2[q]);
-                ln_sum += t.x + t.y;
-                ln_sq = fmaf(t.x, t.x, fmaf(t.y, t.y, ln_sq));
-              }
-            }
             sts128(stg + (uint32_t)lane * 128 + (uint32_t)((j ^ (lane & 7)) << 4), ov);
           }
-          if (!LN && p.tma_store) {
+          if (p.tma_store) {
             // the staged 32 x 128 B tile already has the SWIZZLE_128B layout: hand it to the TMA engine (rows beyond M
             // are clipped by the tensor map) instead of spending 8 LDS + 8 STG per lane on it
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -513,10 +428,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
         }
       }
-      if (VL && p.vl.out_stats && row_ok) {                  // this warp's 128 columns of this row
-        float2* op = reinterpret_cast<float2*>(p.vl.out_stats) + ((int64_t)b * p.M + row) * (p.n_blocks * 2) + n_blk * 2 + half;
-        *op = make_float2(vs_sum, vs_sq);
-      }
       // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator back
       tcgen05_fence_before();
       __syncwarp();
@@ -526,58 +437,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
 
-      if (LN && n_blk == p.n_blocks - 1) {
-        // ---- fused LayerNorm: all N columns of this m-block have been written (by this CTA's epilogue warps, still in
-        // L2).  Combine the two column halves' row statistics, then normalise this warp's 32 rows x (n_blocks x 128)
-        // columns in place with coalesced 16 B accesses.
-        const int rloc = quarter * 32 + lane;
-        sstat[(half * 128 + rloc) * 2] = ln_sum;
-        sstat[(half * 128 + rloc) * 2 + 1] = ln_sq;
-        __threadfence_block();                               // this warp's global stores precede its loads below
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        const float tot = ln_sum + sstat[((half ^ 1) * 128 + rloc) * 2];
-        const float tsq = ln_sq + sstat[((half ^ 1) * 128 + rloc) * 2 + 1];
-        const float inv_n = 1.0f / (float)p.N;
-        const float mean = tot * inv_n;
-        const float rstd = rsqrtf(fmaxf(tsq * inv_n - mean * mean, 0.f) + p.ln_eps);
-        ln_sum = 0.f; ln_sq = 0.f;
-        const float* gam = p.ln_gamma + (int64_t)b * p.N;
-        const float* bet = p.ln_beta + (int64_t)b * p.N;
-        bf16* cbase = (bf16*)p.C + b * p.c_bstride + lp * 8;
-        for (int nb = 0; nb < p.n_blocks; nb++) {
-#pragma unroll
-          for (int sp = 0; sp < COLS_PER_WARP / 64; sp++) {
-            const int64_t c0 = (int64_t)nb * BN + half * COLS_PER_WARP + sp * 64 + lp * 8;   // this lane's 8 columns
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gam + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gam + c0 + 4));
-            const float4 e0 = __ldg(reinterpret_cast<const float4*>(bet + c0)), e1 = __ldg(reinterpret_cast<const float4*>(bet + c0 + 4));
-            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float bb[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-            uint4 raw[8];
-#pragma unroll
-            for (int i8 = 0; i8 < 8; i8++) {               // 8 independent 16 B loads in flight (L2 hits)
-              const int64_t rg = row_base + i8 * 4 + lr;
-              raw[i8] = rg < p.M ? __ldcg(reinterpret_cast<const uint4*>(cbase + rg * p.ldc + (c0 - lp * 8))) : make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int i8 = 0; i8 < 8; i8++) {
-              const int rr = i8 * 4 + lr;
-              const float mu = __shfl_sync(0xffffffffu, mean, rr);
-              const float rs = __shfl_sync(0xffffffffu, rstd, rr);
-              const int64_t rg = row_base + rr;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&raw[i8]);
-#pragma unroll
-              for (int q = 0; q < 4; q++) {
-                float2 t = __bfloat1622float2(h2[q]);
-                t.x = fmaf((t.x - mu) * rs, gg[2 * q], bb[2 * q]);
-                t.y = fmaf((t.y - mu) * rs, gg[2 * q + 1], bb[2 * q + 1]);
-                h2[q] = __floats2bfloat162_rn(t.x, t.y);
-              }
-              if (rg < p.M) *reinterpret_cast<uint4*>(cbase + rg * p.ldc + (c0 - lp * 8)) = raw[i8];
-            }
-          }
-        }
-        __syncwarp();
-      }
     }
   }
 
@@ -657,13 +516,13 @@ static int make_map_c(cir_ctx* ctx, CUtensorMap* map, const void* base, int64_t 
   return cir_make_map_3d(ctx, map, base, N, M, batch, ldc, c_bstride, 64, 32, 1);
 }
 
-template <int BN, bool PAIR, bool LN, bool VL = false, bool FILT = false>
+template <int BN, bool PAIR, bool FILT = false>
 static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc) {
   using C = tc::Cfg<BN, PAIR>;
   const unsigned bit = FILT ? 1u << (26 + (BN == 128 ? 0 : 1) + (PAIR ? 1 : 0))
-                            : 1u << (8 + (BN == 128 ? 0 : 1) + (PAIR ? 2 : 0) + (LN ? 4 : 0) + (VL ? 8 : 0));   // per context: the attribute is per device
+                            : 1u << (8 + (BN == 128 ? 0 : 1) + (PAIR ? 2 : 0));   // per context: the attribute is per device
   if (!(ctx->func_attr_mask & bit)) {
-    CIR_CUDA(cudaFuncSetAttribute(tc::gemm_tcgen05_kernel<BN, PAIR, LN, VL, FILT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES + (VL ? C::VL_BYTES : 0)));
+    CIR_CUDA(cudaFuncSetAttribute(tc::gemm_tcgen05_kernel<BN, PAIR, FILT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     ctx->func_attr_mask |= bit;
   }
   const int slots = PAIR ? ctx->num_sms / 2 : ctx->num_sms;
@@ -671,7 +530,7 @@ static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, c
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(PAIR ? 2 * workers : workers);
   cfg.blockDim = dim3(tc::THREADS);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES + (VL ? C::VL_BYTES : 0);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -681,16 +540,11 @@ static int launch_tc(cir_ctx* ctx, const tc::Params& p, const CUtensorMap& ma, c
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cir_prof_gemm_begin(ctx, 2.0 * (double)p.M * (double)p.N * (double)p.K * (double)p.batch);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_tcgen05_kernel<BN, PAIR, LN, VL, FILT>, ma, mw, mc, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_tcgen05_kernel<BN, PAIR, FILT>, ma, mw, mc, p);
   cir_prof_gemm_end(ctx);
   if (e != cudaSuccess) { cir_set_error("tcgen05 GEMM launch failed: %s", cudaGetErrorString(e)); return CIR_ECUDA; }
   CIR_LAUNCH_CHECK(ctx);
   return CIR_OK;
-}
-
-bool cir_gemm_uses_pair(const cir_ctx* ctx, int64_t M, int64_t N, int batch) {
-  const int64_t pair_tiles = ((M + 2 * tc::BM - 1) / (2 * tc::BM)) * ((N + 255) / 256) * batch;
-  return ctx->gemm_pair && pair_tiles >= ctx->num_sms / 2;
 }
 
 int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a) {
@@ -716,7 +570,7 @@ int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a) {
   const int64_t tiles256 = ((a->M + tc::BM - 1) / tc::BM) * ((a->N + 255) / 256) * a->batch;
   const int64_t pair_tiles = ((a->M + 2 * tc::BM - 1) / (2 * tc::BM)) * ((a->N + 255) / 256) * a->batch;
   const bool use_pair = ctx->gemm_pair && pair_tiles >= ctx->num_sms / 2;
-  const bool use128 = !use_pair && !a->ln && ((a->N <= 128) || (tiles256 < ctx->num_sms));
+  const bool use128 = !use_pair && ((a->N <= 128) || (tiles256 < ctx->num_sms));
   const int BN = use128 ? 128 : 256;
   const int tile_m = use_pair ? 2 * tc::BM : tc::BM;
   p.m_blocks = (int32_t)((a->M + tile_m - 1) / tile_m);
@@ -725,33 +579,20 @@ int cir_gemm_tcgen05(cir_ctx* ctx, const cir_gemm_args* a) {
   const int64_t nt = (int64_t)p.m_blocks * p.n_blocks * a->batch;
   CIR_CHECK_ARG(nt < (1ll << 31), "tcgen05 GEMM: too many tiles");
   p.num_tiles = (int32_t)nt;
-  p.ln_gamma = ctx->ln_gamma; p.ln_beta = ctx->ln_beta; p.ln_eps = ctx->ln_eps;
-  p.ln_fuse = (ctx->ln_gamma != nullptr) ? 1 : 0;
-  if (p.ln_fuse) {
-    CIR_CHECK_ARG(use_pair && !a->c_f32 && a->N == 768 && (a->ldc % 8) == 0 && a->act == CIR_ACT_NONE,
-                  "fused LayerNorm needs a pair-tile GEMM with N = 768 and a bf16 output");
-  }
   CUtensorMap ma, mw;
   CIR_TRY(cir_make_map_2d(ctx, &ma, a->A, a_rows, a->K, a->lda, tc::BM));
   CIR_TRY(cir_make_map_2d(ctx, &mw, a->W, w_rows, a->K, a->ldw, use_pair ? BN / 2 : BN));
   // bf16 outputs leave through TMA stores when the C layout is expressible as a tensor map (16 B aligned strides)
   CUtensorMap mc = ma;
   p.tma_store = 0;
-  if (ctx->gemm_tma_store && !a->c_f32 && !p.ln_fuse && (a->ldc % 8) == 0 && (a->N % 64) == 0 && ((uintptr_t)a->C & 15) == 0 &&
+  if (ctx->gemm_tma_store && !a->c_f32 && (a->ldc % 8) == 0 && (a->N % 64) == 0 && ((uintptr_t)a->C & 15) == 0 &&
       (a->batch == 1 || (a->c_bstride % 8) == 0) && a->M < (1ll << 31)) {
     CIR_TRY(make_map_c(ctx, &mc, a->C, a->N, a->M, a->batch, a->ldc, a->c_bstride));
     p.tma_store = 1;
   }
-  if (a->ln) {
-    CIR_CHECK_ARG(!p.ln_fuse && !use128 && !a->c_f32 && (a->ldc % 8) == 0 && (a->N % 64) == 0, "virtual LayerNorm needs 256-wide tiles and a bf16 output with N % 64 == 0");
-    CIR_CHECK_ARG(!a->ln->out_stats || (a->N % 256) == 0, "virtual LayerNorm: out_stats needs N % 256 == 0");
-    CIR_CHECK_ARG(!a->ln->res_stats || (a->residual && !a->res_f32 && (a->ldres % 8) == 0), "virtual LayerNorm: res_stats needs a bf16 residual with ldres % 8 == 0");
-    p.vl = *a->ln;
-    return use_pair ? launch_tc<256, true, false, true>(ctx, p, ma, mw, mc) : launch_tc<256, false, false, true>(ctx, p, ma, mw, mc);
-  }
-  if (use_pair) return p.ln_fuse ? launch_tc<256, true, true>(ctx, p, ma, mw, mc) : launch_tc<256, true, false>(ctx, p, ma, mw, mc);
-  if (use128) return launch_tc<128, false, false>(ctx, p, ma, mw, mc);
-  return launch_tc<256, false, false>(ctx, p, ma, mw, mc);
+  if (use_pair) return launch_tc<256, true>(ctx, p, ma, mw, mc);
+  if (use128) return launch_tc<128, false>(ctx, p, ma, mw, mc);
+  return launch_tc<256, false>(ctx, p, ma, mw, mc);
 }
 
 // Similarity tiles with a threshold filter instead of an output matrix (stage-I top-K): S = A W^T is computed tile by tile on the
@@ -776,5 +617,5 @@ int cir_gemm_tcgen05_filter(cir_ctx* ctx, const void* A, const void* W, int64_t 
   CUtensorMap ma, mw;
   CIR_TRY(cir_make_map_2d(ctx, &ma, A, M, K, K, tc::BM));
   CIR_TRY(cir_make_map_2d(ctx, &mw, W, N, K, K, use_pair ? 128 : 256));
-  return use_pair ? launch_tc<256, true, false, false, true>(ctx, p, ma, mw, ma) : launch_tc<256, false, false, false, true>(ctx, p, ma, mw, ma);
+  return use_pair ? launch_tc<256, true, true>(ctx, p, ma, mw, ma) : launch_tc<256, false, true>(ctx, p, ma, mw, ma);
 }

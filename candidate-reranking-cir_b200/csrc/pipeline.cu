@@ -79,9 +79,6 @@ extern "C" int cir_create(cir_ctx** out, int device, int dtype) {
   c->stage1_tc = 1;
   c->gemm_tma_store = 1;
   c->func_attr_mask = 0;
-  c->virtual_ln = 0;
-  c->fuse_ln = 0;   // measured on B200: no gain over the separate HBM-bound LayerNorm kernels, so opt-in
-  c->ln_gamma = nullptr; c->ln_beta = nullptr; c->ln_eps = 0.f;
   c->stream = 0;
   c->num_sms = prop.multiProcessorCount;
   c->launches = 0;
@@ -141,8 +138,6 @@ extern "C" int cir_set_prune_last_layer(cir_ctx* ctx, int enable) { ctx->prune_l
 extern "C" int cir_set_dedup_first_layer(cir_ctx* ctx, int enable) { ctx->dedup_first = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_set_fuse_qkv_attention(cir_ctx* ctx, int enable) { ctx->fuse_qkv = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_set_stage1_tensor_cores(cir_ctx* ctx, int enable) { ctx->stage1_tc = enable ? 1 : 0; return CIR_OK; }
-extern "C" int cir_set_fuse_layernorm(cir_ctx* ctx, int enable) { ctx->fuse_ln = enable ? 1 : 0; return CIR_OK; }
-extern "C" int cir_set_virtual_layernorm(cir_ctx* ctx, int enable) { ctx->virtual_ln = enable; return CIR_OK; }   // 1 both, 2 self-LN only, 3 FFN-LN only
 extern "C" int cir_set_gemm_tma_store(cir_ctx* ctx, int enable) { ctx->gemm_tma_store = enable ? 1 : 0; return CIR_OK; }
 extern "C" int cir_get_dtype(const cir_ctx* ctx) { return ctx->dtype; }
 extern "C" int64_t cir_launch_count(cir_ctx* ctx, int reset) {
@@ -156,7 +151,6 @@ extern "C" int cir_gemm(cir_ctx* ctx, const cir_gemm_args* a) {
   CIR_CHECK_ARG(a && a->A && a->W && a->C, "gemm: null operand");
   CIR_CHECK_ARG(a->M >= 0 && a->N >= 0 && a->K > 0 && a->batch >= 0, "gemm: bad shape M=%lld N=%lld K=%lld", (long long)a->M, (long long)a->N, (long long)a->K);
   const bool tc = ctx->dtype == CIR_DTYPE_BF16 && ctx->gemm_impl != CIR_GEMM_SIMT;
-  CIR_CHECK_ARG(!a->ln || tc, "gemm: the virtual-LayerNorm extension needs the tcgen05 path (bf16 context)");
   return tc ? cir_gemm_tcgen05(ctx, a) : cir_gemm_simt(ctx, a);
 }
 
@@ -178,9 +172,8 @@ struct Bump {
 // thin wrapper: C[batch][M,N] = act(A W^T + bias) (+res)
 int gemm(cir_ctx* ctx, const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw, int64_t w_bs, const float* bias,
          int64_t bias_bs, void* C, int64_t ldc, int64_t c_bs, int c_f32, const void* res, int64_t ldres, int64_t res_bs, int res_f32,
-         int64_t M, int64_t N, int64_t K, int batch, int act, const cir_gemm_ln* ln = nullptr) {
+         int64_t M, int64_t N, int64_t K, int batch, int act) {
   cir_gemm_args g{};
-  g.ln = ln;
   g.A = A; g.W = W; g.C = C; g.bias = bias; g.residual = res;
   g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldc = ldc; g.ldres = ldres;
   g.a_bstride = a_bs; g.w_bstride = w_bs; g.c_bstride = c_bs; g.bias_bstride = bias_bs; g.res_bstride = res_bs;
@@ -190,24 +183,14 @@ int gemm(cir_ctx* ctx, const void* A, int64_t lda, int64_t a_bs, const void* W, 
 
 inline char* at(void* p, int64_t elems, size_t esz) { return (char*)p + elems * (int64_t)esz; }
 
-// y = LayerNorm(A W^T + bias + res) with per-batch gamma/beta [batch][N=768], rows contiguous (ld = 768).
-// bf16 mode with a pair-tile GEMM: ONE kernel (statistics and in-place normalisation inside the GEMM epilogue);
-// otherwise GEMM into `pre` followed by the LayerNorm kernel.
+// y = LayerNorm(A W^T + bias + res) with per-batch gamma/beta [batch][N=768], rows contiguous (ld = 768): GEMM into `pre`
+// (residual added in its epilogue) followed by the LayerNorm kernel.  Two fusions were built and measured in rounds 1-2 (statistics +
+// in-place pass inside the GEMM epilogue; "virtual" LayerNorm folded into the consumer GEMMs): both lost to this form on the
+// power-capped board (65.1-67.1 k vs 68.0 k triplets/s) and were removed -- DESIGN.md section 5.
 int gemm_layernorm(cir_ctx* ctx, const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw, int64_t w_bs, const float* bias,
                    int64_t bias_bs, const void* res, int64_t ldres, int64_t res_bs, const float* gamma, const float* beta, float eps,
                    void* pre, void* y, int64_t M, int64_t K, int batch) {
   const int64_t D_ = CIR_HIDDEN;
-  // Fusing pays only where the epilogue has slack: with K = 3072 (FFN2) a tile's MMAs take 4x longer than its epilogue,
-  // so the in-place normalisation pass is free; with K = 768 the epilogue is already the pacing stage and the extra
-  // pass costs more than the separate (HBM-bound) LayerNorm kernel it would replace (measured).
-  const bool fused = ctx->dtype == CIR_DTYPE_BF16 && ctx->fuse_ln && ctx->gemm_impl != CIR_GEMM_SIMT && (K % 8) == 0 && K >= 2048 &&
-                     cir_gemm_uses_pair(ctx, M, D_, batch);
-  if (fused) {
-    ctx->ln_gamma = gamma; ctx->ln_beta = beta; ctx->ln_eps = eps;
-    const int rc = gemm(ctx, A, lda, a_bs, W, ldw, w_bs, bias, bias_bs, y, D_, M * D_, 0, res, ldres, res_bs, 0, M, D_, K, batch, CIR_ACT_NONE);
-    ctx->ln_gamma = nullptr; ctx->ln_beta = nullptr;
-    return rc;
-  }
   CIR_TRY(gemm(ctx, A, lda, a_bs, W, ldw, w_bs, bias, bias_bs, pre, D_, M * D_, 0, res, ldres, res_bs, 0, M, D_, K, batch, CIR_ACT_NONE));
   return cir_add_layernorm(ctx, pre, 0, (int64_t)batch * M, nullptr, gamma, beta, M, y, 0, (int64_t)batch * M, eps);
 }
@@ -380,8 +363,7 @@ extern "C" int cir_stage1_gallery_embed(cir_ctx* ctx, const cir_stage1_weights* 
 }
 
 // ========================================================================================== stage II
-struct S2Ws { void *cand, *kv, *emb, *h, *qkv, *ctx, *pre, *a, *qc, *ctxc, *m, *x, *f, *feats; float *hid, *st1, *st3; size_t total; };
-constexpr int VLN_PARTS = (int)(CIR_HIDDEN / 128);    // partial row statistics per 768-wide row (cir_gemm_ln.out_stats)
+struct S2Ws { void *cand, *kv, *emb, *h, *qkv, *ctx, *pre, *a, *qc, *ctxc, *m, *x, *f, *feats; float *hid; size_t total; };
 static S2Ws s2_plan(const cir_ctx* ctx, void* ws, size_t bytes, int64_t T, int64_t C, int64_t Q, int64_t L, int64_t N) {
   const size_t es = act_size(ctx);
   const int64_t M = T * L;
@@ -402,8 +384,6 @@ static S2Ws s2_plan(const cir_ctx* ctx, void* ws, size_t bytes, int64_t T, int64
   w.f = b.take(2 * M * F * es);
   w.feats = b.take(T * 2 * D * es);
   w.hid = (float*)b.take(T * D * 4);
-  w.st1 = (float*)b.take(2 * M * VLN_PARTS * 2 * 4);
-  w.st3 = (float*)b.take(2 * M * VLN_PARTS * 2 * 4);
   w.total = align_up(b.off, 256);
   return w;
 }
@@ -494,12 +474,6 @@ static int stage2_score_impl(cir_ctx* ctx, const cir_stage2_weights* w, const vo
     CIR_TRY(cir_gather_rows(ctx, z_t, trip_query, ws.h, T, L * D));
     CIR_TRY(cir_gather_rows(ctx, ws.emb, trip_query, at(ws.h, M * D, es), T, L * D));
   }
-  // Virtual LayerNorm (cir_gemm_ln): the self-attention LayerNorm{A,B} and the FFN LayerNorm of the full layers are never
-  // stored.  ws.a / ws.h then hold the RAW GEMM outputs, st1 / st3 their partial row statistics; consumers normalise
-  // in their epilogues (folded weights vcq_* / vq_*), only the cross-attention LayerNorm stays a kernel.
-  const bool vln = ctx->virtual_ln && ctx->dtype == CIR_DTYPE_BF16 && ctx->gemm_impl != CIR_GEMM_SIMT && w->vcq_w[0] && w->vq_w[1];
-  const bool vln1 = vln && ctx->virtual_ln != 3, vln3 = vln && ctx->virtual_ln != 2;
-  bool h_raw = false;                                         // ws.h = raw FFN output of the previous layer (+ st3)
   for (int i = 0; i < full_layers; i++) {                                                                          // nlvr_encoder.py:506
     const bool per_query = dedup0 && i == 0;
     if (per_query) {
@@ -518,50 +492,13 @@ static int stage2_score_impl(cir_ctx* ctx, const cir_stage2_weights* w, const vo
       }
     } else {
     // ---- twin self-attention (:281-289, :346-363): separate weights per stream, shared padding mask (:774)
-    if (h_raw) {
-      cir_gemm_ln e{};
-      e.a_stats = ws.st3; e.a_colsum = w->vq_colsum[i]; e.colsum_bstride = 3 * D; e.a_parts = VLN_PARTS; e.a_width = (int32_t)D; e.eps = BERT_EPS;
-      CIR_TRY(gemm(ctx, ws.h, D, M * D, w->vq_w[i], D, 3 * D * D, w->vq_b[i], 3 * D, ws.qkv, 3 * D, M * 3 * D, 0,
-                   nullptr, 0, 0, 0, M, 3 * D, D, 2, CIR_ACT_NONE, &e));
-    } else {
-      CIR_TRY(self_attention(ctx, ws.h, w->self_qkv_w[i], w->self_qkv_b[i], 2, mask, trip_query, T, L, ws.qkv, ws.ctx));
-    }
-    if (h_raw) {
-      for (int s = 0; s < 2; s++) {
-        cir_attn_args a{};
-        void* qkv_s = at(ws.qkv, s * M * 3 * D, es);
-        a.q = qkv_s; a.k = at(qkv_s, D, es); a.v = at(qkv_s, 2 * D, es); a.o = at(ws.ctx, s * M * D, es);
-        a.q_bs = a.k_bs = a.v_bs = L * 3 * D; a.q_rs = a.k_rs = a.v_rs = 3 * D; a.o_bs = L * D; a.o_rs = D;
-        a.key_mask = mask; a.mask_index = trip_query;
-        a.B = (int32_t)T; a.H = CIR_HEADS; a.Lq = (int32_t)L; a.Lk = (int32_t)L; a.scale = 0.125f;                  // / sqrt(64) (:193)
-        CIR_TRY(cir_attention(ctx, &a));
-      }
-    }
+    CIR_TRY(self_attention(ctx, ws.h, w->self_qkv_w[i], w->self_qkv_b[i], 2, mask, trip_query, T, L, ws.qkv, ws.ctx));
     // a_s = LayerNorm{A,B}(dense_s(ctx_s) + h_s)   (:261-264)
-    if (vln1 || h_raw) {                                       // ws.a = raw dense_s(ctx_s) + h_s, st1 = its row statistics
-      cir_gemm_ln e{};
-      e.out_stats = vln1 ? ws.st1 : nullptr; e.eps = BERT_EPS;
-      if (h_raw) {
-        e.res_stats = ws.st3; e.res_gamma = w->ffn_ln_g[i - 1]; e.res_beta = w->ffn_ln_b[i - 1]; e.gb_bstride = 0;
-        e.res_parts = VLN_PARTS; e.res_width = (int32_t)D;
-      }
-      CIR_TRY(gemm(ctx, ws.ctx, D, M * D, w->self_out_w[i], D, D * D, w->self_out_b[i], D, vln1 ? ws.a : ws.pre, D, M * D, 0, ws.h, D, M * D, 0,
-                   M, D, D, 2, CIR_ACT_NONE, &e));
-      if (!vln1) CIR_TRY(cir_add_layernorm(ctx, ws.pre, 0, 2 * M, nullptr, w->self_ln_g[i], w->self_ln_b[i], M, ws.a, 0, 2 * M, BERT_EPS));
-    } else {
-      CIR_TRY(gemm_layernorm(ctx, ws.ctx, D, M * D, w->self_out_w[i], D, D * D, w->self_out_b[i], D, ws.h, D, M * D,
-                             w->self_ln_g[i], w->self_ln_b[i], BERT_EPS, ws.pre, ws.a, M, D, 2));
-    }
+    CIR_TRY(gemm_layernorm(ctx, ws.ctx, D, M * D, w->self_out_w[i], D, D * D, w->self_out_b[i], D, ws.h, D, M * D,
+                           w->self_ln_g[i], w->self_ln_b[i], BERT_EPS, ws.pre, ws.a, M, D, 2));
     // ---- twin cross-attention onto the SAME candidate tokens (:322-339)
-    if (vln1) {
-      cir_gemm_ln e{};
-      e.a_stats = ws.st1; e.a_colsum = w->vcq_colsum[i]; e.colsum_bstride = D; e.a_parts = VLN_PARTS; e.a_width = (int32_t)D; e.eps = BERT_EPS;
-      CIR_TRY(gemm(ctx, ws.a, D, M * D, w->vcq_w[i], D, D * D, w->vcq_b[i], D, ws.qc, D, M * D, 0, nullptr, 0, 0, 0,
-                   M, D, D, 2, CIR_ACT_NONE, &e));
-    } else {
-      CIR_TRY(gemm(ctx, ws.a, D, M * D, w->cross_q_w[i], D, D * D, w->cross_q_b[i], D, ws.qc, D, M * D, 0, nullptr, 0, 0, 0,
-                   M, D, D, 2, CIR_ACT_NONE));
-    }
+    CIR_TRY(gemm(ctx, ws.a, D, M * D, w->cross_q_w[i], D, D * D, w->cross_q_b[i], D, ws.qc, D, M * D, 0, nullptr, 0, 0, 0,
+                 M, D, D, 2, CIR_ACT_NONE));
     }   // !per_query
     // K/V projections once per candidate image: rows K0|V0|K1|V1 (:158-159)
     CIR_TRY(gemm(ctx, ws.cand, D, 0, w->cross_kv_w[i], D, 0, w->cross_kv_b[i], 0, ws.kv, 4 * D, 0, 0, nullptr, 0, 0, 0,
@@ -580,24 +517,11 @@ static int stage2_score_impl(cir_ctx* ctx, const cir_stage2_weights* w, const vo
     // m = merge(dense0(c0), dense1(c1)) folded into one K=1536 GEMM (:250-258); x_s = LayerNorm{A,B}(m + a_s) (:256,:260)
     CIR_TRY(gemm(ctx, ws.ctxc, 2 * D, 0, w->cross_out_w[i], 2 * D, 0, w->cross_out_b[i], 0, ws.m, D, 0, 0, nullptr, 0, 0, 0,
                  M, D, 2 * D, 1, CIR_ACT_NONE));
-    if (vln1 && !per_query) {                                  // a_s = LN(raw) on the fly from st1
-      CIR_TRY(cir_ln_cross_virtual(ctx, ws.a, ws.st1, VLN_PARTS, w->self_ln_g[i], w->self_ln_b[i], ws.m, M, w->cross_ln_g[i],
-                                   w->cross_ln_b[i], M, ws.x, 2 * M, BERT_EPS));
-    } else {
-      CIR_TRY(cir_add_layernorm(ctx, ws.m, 0, M, ws.a, w->cross_ln_g[i], w->cross_ln_b[i], M, ws.x, 0, 2 * M, BERT_EPS));
-    }
+    CIR_TRY(cir_add_layernorm(ctx, ws.m, 0, M, ws.a, w->cross_ln_g[i], w->cross_ln_b[i], M, ws.x, 0, 2 * M, BERT_EPS));
     // ---- FFN, weights shared by both streams (:469-476): both streams as 2M rows
     CIR_TRY(gemm(ctx, ws.x, D, 0, w->ffn1_w[i], D, 0, w->ffn1_b[i], 0, ws.f, F, 0, 0, nullptr, 0, 0, 0, 2 * M, F, D, 1, CIR_ACT_GELU));
-    if (vln3 && i + 1 < full_layers) {                         // ws.h = raw FFN output + x, st3 = its row statistics
-      cir_gemm_ln e{};
-      e.out_stats = ws.st3; e.eps = BERT_EPS;
-      CIR_TRY(gemm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.h, D, 0, 0, ws.x, D, 0, 0, 2 * M, D, F, 1, CIR_ACT_NONE, &e));
-      h_raw = true;
-    } else {
-      CIR_TRY(gemm_layernorm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.x, D, 0, w->ffn_ln_g[i], w->ffn_ln_b[i], BERT_EPS,
-                             ws.pre, ws.h, 2 * M, F, 1));
-      h_raw = false;
-    }
+    CIR_TRY(gemm_layernorm(ctx, ws.f, F, 0, w->ffn2_w[i], F, 0, w->ffn2_b[i], 0, ws.x, D, 0, w->ffn_ln_g[i], w->ffn_ln_b[i], BERT_EPS,
+                           ws.pre, ws.h, 2 * M, F, 1));
   }
   if (ctx->prune_last) {
     // ---- last layer, CLS rows only.  The encoder returns cat(h0[:,0,:], h1[:,0,:]) (nlvr_encoder.py:906-909), so

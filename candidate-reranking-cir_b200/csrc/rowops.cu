@@ -156,31 +156,6 @@ add_layernorm_kernel(const TX* __restrict__ x, int64_t x_rows, const TR* __restr
   }
 }
 
-// y[r] = LN2( m[r % m_rows] + LN1(raw[r]) ): LN1's statistics come as partial (sum, sum of squares) pairs written by the
-// GEMM that produced `raw` (cir_gemm_ln.out_stats), so LN1(raw) is never stored.  bf16 only.
-__global__ void __launch_bounds__(WARPS * 32)
-ln_cross_virtual_kernel(const bf16* __restrict__ raw, const float2* __restrict__ stats, int parts, const float* __restrict__ g1,
-                        const float* __restrict__ b1, const bf16* __restrict__ m, int64_t m_rows, const float* __restrict__ g2,
-                        const float* __restrict__ b2, int64_t rows_per_group, bf16* __restrict__ y, int64_t rows, float eps) {
-  const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (r >= rows) return;
-  float v[PER_LANE], t[PER_LANE], g[PER_LANE], b[PER_LANE];
-  load_row<bf16>(raw + r * D, lane, v);
-  load_row<bf16>(m + (r % m_rows) * D, lane, t);
-  float s1 = 0.f, s2 = 0.f;
-  for (int i = 0; i < parts; i++) { const float2 q = __ldg(stats + r * parts + i); s1 += q.x; s2 += q.y; }
-  const float mu = s1 * (1.0f / D);
-  const float rstd = rsqrtf(fmaxf(s2 * (1.0f / D) - mu * mu, 0.f) + eps);
-  const int64_t grp = r / rows_per_group;
-  load_row<float>(g1 + grp * D, lane, g);
-  load_row<float>(b1 + grp * D, lane, b);
-#pragma unroll
-  for (int i = 0; i < PER_LANE; i++) v[i] = fmaf((v[i] - mu) * rstd, g[i], b[i]) + t[i];
-  layernorm24(v, g2 + grp * D, b2 + grp * D, eps, lane);
-  store_row<bf16>(y + r * D, lane, v);
-}
-
 template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
 bert_embeddings_kernel(const int32_t* __restrict__ ids, int64_t rows, int64_t L, const float* __restrict__ word,
@@ -318,17 +293,6 @@ extern "C" int cir_add_layernorm(cir_ctx* ctx, const void* x, int x_f32, int64_t
   else LN_LAUNCH(bf16, bf16, bf16);
 #undef LN_LAUNCH
   cir_prof_end(ctx);
-  CIR_LAUNCH_CHECK(ctx);
-  return CIR_OK;
-}
-
-// internal (pipeline.cu): the cross-attention LayerNorm of the virtual-LayerNorm path
-int cir_ln_cross_virtual(cir_ctx* ctx, const void* raw, const float* stats, int parts, const float* g1, const float* b1, const void* m,
-                         int64_t m_rows, const float* g2, const float* b2, int64_t rows_per_group, void* y, int64_t rows, float eps) {
-  if (rows == 0) return CIR_OK;
-  CIR_CHECK_ARG(ctx->dtype == CIR_DTYPE_BF16, "ln_cross_virtual: bf16 only");
-  ln_cross_virtual_kernel<<<row_blocks(rows), WARPS * 32, 0, ctx->stream>>>((const bf16*)raw, (const float2*)stats, parts, g1, b1, (const bf16*)m,
-                                                                            m_rows, g2, b2, rows_per_group, (bf16*)y, rows, eps);
   CIR_LAUNCH_CHECK(ctx);
   return CIR_OK;
 }

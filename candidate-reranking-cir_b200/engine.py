@@ -76,14 +76,6 @@ class Engine:
         """bf16, G >= 16,384: stage-I top-K filters candidates on the tensor cores and re-checks them in fp32 (default on; bit-equal)."""
         N.check(self._lib.cir_set_stage1_tensor_cores(self.ctx, 1 if enable else 0))
 
-    def set_virtual_layernorm(self, enable: bool):
-        """stage II: never materialise the self-attention / FFN LayerNorms (cir_gemm_ln); bf16 only."""
-        N.check(self._lib.cir_set_virtual_layernorm(self.ctx, int(enable)))
-
-    def set_fuse_layernorm(self, enable: bool):
-        """bf16 mode: LayerNorm inside the FFN2 GEMM epilogue (opt-in; default is the separate LayerNorm kernel)."""
-        N.check(self._lib.cir_set_fuse_layernorm(self.ctx, 1 if enable else 0))
-
     def profile_gemm(self, enable: bool):
         N.check(self._lib.cir_profile_gemm(self.ctx, 1 if enable else 0))
 
@@ -262,43 +254,7 @@ class Engine:
         self._sync_stream()
         N.check(self._lib.cir_pack_stage2_weights(self.ctx, C.byref(st), N.ptr(blob), blob.numel(), C.byref(w)), "cir_pack_stage2_weights")
         torch.cuda.synchronize(self.device)
-        keep: List[torch.Tensor] = [blob]
-        if self.precision == "bf16":
-            self._pack_virtual_ln(sd, w, keep)          # optional folded copies for cir_set_virtual_layernorm (host-side, experimental switch)
-        return w, keep
-
-    def _fold_ln(self, Ws, bs, gammas, betas, keep):
-        """LN(x) W^T + b == rstd (x W'^T) - rstd mu colsum + b'  with W' = W diag(gamma) (rounded to bf16, and colsum
-        taken from the ROUNDED values so that the mean term cancels exactly), b' = b + W beta.  float64 composition.
-        Ws/bs/gammas/betas: per-batch lists -> (ptr W' [B][N,K] bf16, ptr b' [B][N], ptr colsum [B][N])."""
-        Wf, bf, cs = [], [], []
-        for W, b, g, be in zip(Ws, bs, gammas, betas):
-            W, b, g, be = W.double(), b.double(), g.double(), be.double()
-            Wr = (W * g[None, :]).to(torch.bfloat16)
-            Wf.append(Wr)
-            cs.append(Wr.double().sum(dim=1))
-            bf.append(b + W @ be)
-        tw = torch.stack(Wf).to(self.device).contiguous()
-        tb = torch.stack(bf).float().to(self.device).contiguous()
-        tc = torch.stack(cs).float().to(self.device).contiguous()
-        keep += [tw, tb, tc]
-        return N.ptr(tw), N.ptr(tb), N.ptr(tc)
-
-    def _pack_virtual_ln(self, sd, w, keep):
-        """Folded weight copies for cir_set_virtual_layernorm (include/cir_b200.h, cir_stage2_weights.vq_* / vcq_*)."""
-        for i in range(LAYERS):
-            p = f"text_encoder.encoder.layer.{i}."
-            a, c = p + "attention.", p + "crossattention."
-            ln = [(sd[a + f"output.LayerNorm{x}.weight"], sd[a + f"output.LayerNorm{x}.bias"]) for x in ("A", "B")]
-            w.vcq_w[i], w.vcq_b[i], w.vcq_colsum[i] = self._fold_ln(
-                [sd[c + f"self{s}.query.weight"] for s in (0, 1)], [sd[c + f"self{s}.query.bias"] for s in (0, 1)],
-                [ln[0][0], ln[1][0]], [ln[0][1], ln[1][1]], keep)
-            if i >= 1:
-                q = f"text_encoder.encoder.layer.{i - 1}."
-                g, be = sd[q + "output.LayerNorm.weight"], sd[q + "output.LayerNorm.bias"]
-                Ws = [torch.cat([sd[a + f"self{s}.{n}.weight"] for n in ("query", "key", "value")], dim=0) for s in (0, 1)]
-                bs = [torch.cat([sd[a + f"self{s}.{n}.bias"] for n in ("query", "key", "value")], dim=0) for s in (0, 1)]
-                w.vq_w[i], w.vq_b[i], w.vq_colsum[i] = self._fold_ln(Ws, bs, [g, g], [be, be], keep)
+        return w, [blob]
 
     # ------------------------------------------------------------------ pipelines
     def vit_forward(self, w, images: torch.Tensor, batch: int = 32) -> torch.Tensor:
@@ -570,10 +526,8 @@ class Engine:
         return hits.cpu().tolist() if sync else hits
 
     # ------------------------------------------------------------------ primitive ops (tests)
-    def gemm(self, A, W, bias=None, residual=None, act=N.ACT_NONE, out_f32=False, ln=None):
-        """A [B?,M,K], W [B?,N,K] in act dtype -> C; thin test hook over cir_gemm.
-        ``ln``: dict for the virtual-LayerNorm extension (cir_gemm_ln): a_stats [B,M,P,2] + a_colsum [B,N];
-        res_stats [B,M,P,2] + res_gamma/res_beta [B,N]; out_stats=True -> returns (C, stats [B,M,N/128,2]); eps."""
+    def gemm(self, A, W, bias=None, residual=None, act=N.ACT_NONE, out_f32=False):
+        """A [B?,M,K], W [B?,N,K] in act dtype -> C; thin test hook over cir_gemm."""
         batched = A.dim() == 3
         A3 = A if batched else A[None]
         W3 = W if W.dim() == 3 else W[None]
@@ -597,30 +551,10 @@ class Engine:
         g.batch, g.act = Bn, act
         g.c_f32 = 1 if c_dtype == torch.float32 else 0
         g.res_f32 = 1 if (residual is not None and residual.dtype == torch.float32) else 0
-        keep, stats = [], None
-        if ln is not None:
-            e = N.GemmLn()
-            f32 = lambda t: t.to(self.device, torch.float32).contiguous()
-            if "a_stats" in ln:
-                a_st, a_cs = f32(ln["a_stats"]), f32(ln["a_colsum"]).view(Bn, Nn)
-                e.a_stats, e.a_colsum, e.colsum_bstride = N.ptr(a_st), N.ptr(a_cs), Nn
-                e.a_parts, e.a_width = a_st.shape[-2], K
-                keep += [a_st, a_cs]
-            if "res_stats" in ln:
-                r_st, r_g, r_b = f32(ln["res_stats"]), f32(ln["res_gamma"]).view(Bn, Nn), f32(ln["res_beta"]).view(Bn, Nn)
-                e.res_stats, e.res_gamma, e.res_beta, e.gb_bstride = N.ptr(r_st), N.ptr(r_g), N.ptr(r_b), Nn
-                e.res_parts, e.res_width = r_st.shape[-2], Nn
-                keep += [r_st, r_g, r_b]
-            if ln.get("out_stats"):
-                stats = torch.zeros(Bn, M, Nn // 128, 2, dtype=torch.float32, device=self.device)
-                e.out_stats = N.ptr(stats)
-            e.eps = float(ln.get("eps", 1e-12))
-            g.ln = C.pointer(e)
-            keep.append(e)
         self._sync_stream()
         N.check(self._lib.cir_gemm(self.ctx, C.byref(g)), "cir_gemm")
         out = Cm if batched else Cm[0]
-        return (out, stats) if stats is not None else out
+        return out
 
     def attention(self, q, k, v, key_mask=None, kv_index=None, scale=0.125, work=None, tiles=None):
         """q [B,Lq,H*64], k/v [Bk,Lk,H*64] act dtype -> o [B,Lq,H*64]; test hook over cir_attention."""

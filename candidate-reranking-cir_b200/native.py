@@ -27,18 +27,12 @@ class CirError(RuntimeError):
     pass
 
 
-class GemmLn(C.Structure):
-    _fields_ = [("a_stats", vp), ("a_colsum", vp), ("res_stats", vp), ("res_gamma", vp), ("res_beta", vp), ("out_stats", vp),
-                ("colsum_bstride", i64), ("gb_bstride", i64),
-                ("a_parts", i32), ("a_width", i32), ("res_parts", i32), ("res_width", i32), ("eps", C.c_float)]
-
-
 class GemmArgs(C.Structure):
     _fields_ = [("A", vp), ("W", vp), ("C", vp), ("bias", vp), ("residual", vp),
                 ("M", i64), ("N", i64), ("K", i64),
                 ("lda", i64), ("ldw", i64), ("ldc", i64), ("ldres", i64),
                 ("a_bstride", i64), ("w_bstride", i64), ("c_bstride", i64), ("bias_bstride", i64), ("res_bstride", i64),
-                ("batch", i32), ("act", i32), ("c_f32", i32), ("res_f32", i32), ("ln", C.POINTER(GemmLn))]
+                ("batch", i32), ("act", i32), ("c_f32", i32), ("res_f32", i32)]
 
 
 class AttnArgs(C.Structure):
@@ -113,8 +107,7 @@ class Stage2Weights(C.Structure):
                 ("cross_kv_w", _A), ("cross_kv_b", _A), ("cross_out_w", _A), ("cross_out_b", _A),
                 ("cross_ln_g", _A), ("cross_ln_b", _A), ("ffn1_w", _A), ("ffn1_b", _A),
                 ("ffn2_w", _A), ("ffn2_b", _A), ("ffn_ln_g", _A), ("ffn_ln_b", _A),
-                ("cls0_w", vp), ("cls0_b", vp), ("cls2_w", vp), ("cls2_b", vp),
-                ("vq_w", _A), ("vq_b", _A), ("vq_colsum", _A), ("vcq_w", _A), ("vcq_b", _A), ("vcq_colsum", _A)]
+                ("cls0_w", vp), ("cls0_b", vp), ("cls2_w", vp), ("cls2_b", vp)]
 
 
 _SIGS = {
@@ -129,8 +122,6 @@ _SIGS = {
     "cir_set_dedup_first_layer": (C.c_int, [vp, C.c_int]),
     "cir_set_fuse_qkv_attention": (C.c_int, [vp, C.c_int]),
     "cir_set_stage1_tensor_cores": (C.c_int, [vp, C.c_int]),
-    "cir_set_fuse_layernorm": (C.c_int, [vp, C.c_int]),
-    "cir_set_virtual_layernorm": (C.c_int, [vp, C.c_int]),
     "cir_set_gemm_tma_store": (C.c_int, [vp, C.c_int]),
     "cir_get_dtype": (C.c_int, [vp]),
     "cir_launch_count": (i64, [vp, C.c_int]),

@@ -83,12 +83,6 @@ int  cir_set_fuse_qkv_attention(cir_ctx* ctx, int enable);
  * FILTER candidates with a rigorous error margin, then re-computes the survivors in fp32 -- results are bit-identical to the
  * fp32 path.  Default on; 0 = fp32 CUDA-core similarities for every gallery row. */
 int  cir_set_stage1_tensor_cores(cir_ctx* ctx, int enable);
-/* bf16 mode: fuse LayerNorm into the long-K N=768 pair-tile GEMM epilogue (FFN2): statistics in the epilogue, in-place
- * normalisation pass from L2.  Default OFF: measured 53.7k vs 54.4k triplets/s for the separate LayerNorm kernels. */
-int  cir_set_fuse_layernorm(cir_ctx* ctx, int enable);
-/* 1: cir_stage2_score never materialises the self-attention and FFN LayerNorms of the full layers (bf16 only, needs the
- * folded weight copies of cir_stage2_weights); 0: every LayerNorm is a kernel of its own. */
-int  cir_set_virtual_layernorm(cir_ctx* ctx, int enable);
 /* 1 (default): bf16 GEMM outputs leave the tcgen05 epilogue through TMA bulk tensor stores; 0: per-lane 16 B stores. */
 int  cir_set_gemm_tma_store(cir_ctx* ctx, int enable);
 int  cir_get_dtype(const cir_ctx* ctx);
@@ -120,25 +114,6 @@ int  cir_profile_read(cir_ctx* ctx, int kind, double* total_ms, double* total_wo
  * W: [batch][N, K] act dtype, row stride ldw, batch stride w_bstride
  * C: [batch][M, N] bf16/fp32 (c_f32), row stride ldc, batch stride c_bstride
  * bias: fp32 [batch][N] or NULL; residual: [batch][M,N] (fp32 if res_f32 else act dtype) or NULL */
-/* Optional "virtual LayerNorm" extension of cir_gemm (tcgen05 path, bf16, N % 256 == 0 for out_stats): a LayerNorm
- * between two GEMMs is never materialised.  The producer writes the pre-LN tensor plus partial row statistics
- * (out_stats); the consumer multiplies the RAW tensor with gamma-folded weights and applies the normalisation in its
- * epilogue (a_stats); a GEMM that adds LN(x) as its residual normalises the raw tile on the fly (res_stats).
- * Replaces nn.LayerNorm of src/nlvr_encoder.py:256,260-264,397 without the extra HBM round trip.
- *   statistics: fp32 [batch][M][parts][2] = (sum, sum of squares) over `width / parts` columns each.
- *   a_stats    : C = rstd_r * (A W'^T) - rstd_r mu_r a_colsum[n] + bias[n], with W' = W diag(gamma) (the W passed),
- *                a_colsum[n] = sum_k W'[n,k], bias[n] = b[n] + sum_k W[n,k] beta[k]  (all prepared by the caller)
- *   res_stats  : residual term = (res - mu_r) rstd_r res_gamma[n] + res_beta[n]
- *   out_stats  : partial statistics of the bf16-rounded output, parts = N / 128 */
-typedef struct cir_gemm_ln {
-  const float* a_stats; const float* a_colsum;
-  const float* res_stats; const float* res_gamma; const float* res_beta;
-  float* out_stats;
-  int64_t colsum_bstride, gb_bstride;      /* batch strides of a_colsum and of res_gamma / res_beta (0 = shared) */
-  int32_t a_parts, a_width, res_parts, res_width;
-  float eps;
-} cir_gemm_ln;
-
 typedef struct cir_gemm_args {
   const void* A; const void* W; void* C;
   const float* bias; const void* residual;
@@ -149,7 +124,6 @@ typedef struct cir_gemm_args {
   int32_t act;       /* CIR_ACT_* */
   int32_t c_f32;     /* 1: C is fp32 regardless of ctx dtype */
   int32_t res_f32;   /* 1: residual is fp32 */
-  const cir_gemm_ln* ln;   /* NULL: plain GEMM */
 } cir_gemm_args;
 int cir_gemm(cir_ctx* ctx, const cir_gemm_args* args);
 
@@ -333,12 +307,6 @@ typedef struct cir_stage2_weights {
   const float* ffn_ln_g[CIR_LAYERS];    const float* ffn_ln_b[CIR_LAYERS];
   const void*  cls0_w; const float* cls0_b;      /* [768,1536], [768] */
   const float* cls2_w; const float* cls2_b;      /* row 0 of cls_head.2: [768] fp32, [1] */
-  /* Optional gamma-folded copies for the virtual-LayerNorm path (all NULL = path disabled; see cir_gemm_ln):
-   *   vq_*[i]  : self QKV of layer i >= 1 folded with ffn_ln of layer i-1:  W' = W diag(gamma), colsum[n] = sum_k W'[n,k]
-   *              (of the bf16-rounded W'), bias' = b + W beta.  [2][2304,768] bf16, [2][2304] fp32, [2][2304] fp32
-   *   vcq_*[i] : cross query of layer i folded with self_ln{A,B} of layer i.  [2][768,768], [2][768], [2][768] */
-  const void* vq_w[CIR_LAYERS];  const float* vq_b[CIR_LAYERS];  const float* vq_colsum[CIR_LAYERS];
-  const void* vcq_w[CIR_LAYERS]; const float* vcq_b[CIR_LAYERS]; const float* vcq_colsum[CIR_LAYERS];
 } cir_stage2_weights;
 
 /* BLIP_NLVR.img_txt_fusion_val (src/blip_stage2.py:101-136 -> src/nlvr_encoder.py:777-909) for a

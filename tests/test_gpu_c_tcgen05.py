@@ -134,42 +134,3 @@ def test_tma_store_epilogue_is_bit_identical(e16):
                 e16.set_gemm_tma_store(True)
                 e16.set_gemm_impl(N_.GEMM_AUTO)
             assert torch.equal(tma, lane), (M, N, K, b, kw)
-
-
-def _row_stats(x, parts):
-    """partial (sum, sum of squares) of a [B,M,W] tensor over W/parts columns each -> [B,M,parts,2] fp32"""
-    B, M, W = x.shape
-    xs = x.float().view(B, M, parts, W // parts)
-    return torch.stack([xs.sum(-1), (xs * xs).sum(-1)], dim=-1)
-
-
-@pytest.mark.parametrize("M", [300, 40000])     # single-CTA tiles / CTA-pair tiles
-def test_virtual_layernorm_epilogues(e16, M):
-    """cir_gemm_ln: LN(A) W^T through gamma-folded weights + row statistics, LN(residual) on the fly, output statistics."""
-    torch.manual_seed(0)
-    Bn, K, N = 2, 768, 768
-    eps = 1e-12
-    x = (_rand(Bn, M, K, seed=1) * 1.7 + 0.3).bfloat16()                  # raw (pre-LN) A, non-zero mean
-    gamma, beta = 1.0 + 0.2 * _rand(Bn, K, seed=2), 0.1 * _rand(Bn, K, seed=3)
-    W = _rand(Bn, N, K, seed=4, scale=0.05)
-    bias = _rand(Bn, N, seed=5)
-    res_raw = (_rand(Bn, M, N, seed=6) * 2.0 - 0.5).bfloat16()
-    rg, rb = 1.0 + 0.2 * _rand(Bn, N, seed=7), 0.1 * _rand(Bn, N, seed=8)
-    ln_ref = lambda t, g, b: torch.nn.functional.layer_norm(t.double(), (t.shape[-1],), eps=eps) * g.double()[:, None, :] + b.double()[:, None, :]
-    want = torch.einsum("bmk,bnk->bmn", ln_ref(x, gamma, beta), W.double()) + bias.double()[:, None, :] + ln_ref(res_raw, rg, rb)
-    # caller-side folding (what Engine.pack_stage2 does once per checkpoint)
-    Wf = (W.double() * gamma.double()[:, None, :]).bfloat16()
-    colsum = Wf.double().sum(-1)
-    bias_f = bias.double() + torch.einsum("bnk,bk->bn", W.double(), beta.double())
-    e16.set_gemm_impl(N_.GEMM_TCGEN05)
-    try:
-        out, st = e16.gemm(x, Wf, bias_f.float(), residual=res_raw,
-                           ln=dict(a_stats=_row_stats(x, 6), a_colsum=colsum.float(), res_stats=_row_stats(res_raw, 6),
-                                   res_gamma=rg, res_beta=rb, out_stats=True, eps=eps))
-    finally:
-        e16.set_gemm_impl(N_.GEMM_AUTO)
-    assert out.dtype == torch.bfloat16
-    err = (out.double() - want).abs().max().item()
-    assert err < 4e-2 * max(1.0, want.abs().max().item()), err
-    # the statistics describe exactly the bf16 values that were written
-    assert torch.allclose(st, _row_stats(out, N // 128), rtol=1e-5, atol=1e-3)

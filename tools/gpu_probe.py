@@ -63,13 +63,6 @@ def stage2_probe(T_per=2048, C=48, L=32, reps=3, configs=((1024, 32), (2048, 48)
             ms = timeit(lambda: m2.score_triplets(z_t, ids, mask, tokens, cand), warm=1, it=reps)
             e.set_dedup_first_layer(True)
             print(f"   without first-layer dedup: {ms:.1f} ms -> {Q*K/ms*1e3:.0f} triplets/s", flush=True)
-        for mode in [int(x) for x in os.environ.get("CIR_PROBE_VLN", "").split(",") if x]:
-            e.set_virtual_layernorm(mode)
-            e.launch_count(reset=True)
-            ms = timeit(lambda: m2.score_triplets(z_t, ids, mask, tokens, cand), warm=1, it=reps)
-            nl = e.launch_count() / (reps + 1)
-            e.set_virtual_layernorm(0)
-            print(f"   virtual LayerNorm mode {mode}: {ms:.1f} ms -> {Q*K/ms*1e3:.0f} triplets/s, {nl:.0f} launches/pass", flush=True)
 
 
 def stage1_probe():
