@@ -215,9 +215,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     int acc = 0; uint32_t acc_phase = 0;
     bool tma_store_pending = false;
     int b, m_blk, n_blk;
+    // FILT: slots reserved by the last atomicAdd of this lane and the (column, value) pairs that go there
+    int pend_n = 0, pend_base = 0;
+    uint32_t pend_col[2] = {0u, 0u}, pend_val[2] = {0u, 0u};
+    int64_t pend_row = 0;
+    auto flt_flush = [&]() {
+      if (pend_n > 0) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          if (i < pend_n) {
+            if (pend_base + i < p.flt.cap) p.flt.cand[pend_row * p.flt.cap + pend_base + i] = make_uint2(pend_col[i], pend_val[i]);
+            else *p.flt.overflow = 1;
+          }
+        }
+        pend_n = 0;
+      }
+    };
     for (int it = 0; next_tile(p, worker, num_workers, it, b, m_blk, n_blk); ++it) {
       const int64_t row_base = (int64_t)m_blk * TILE_M + rank * BM + quarter * 32;
       const int64_t row = row_base + lane;
+      if constexpr (FILT) { flt_flush(); pend_row = row; }       // the row changes with the tile: write what the previous tile left pending
       const bool row_ok = row < p.M;
       const int64_t ntile0 = (int64_t)n_blk * BN;
       float flt_thr = INFINITY;
@@ -265,29 +282,59 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tmem_ld_wait();
         if (n00 >= p.N) continue;                          // whole span beyond N (warp-uniform)
         if constexpr (FILT) {
-          // 2 x 32 similarities of this thread's row.  Fast path: one max tree per 32 values.  A chunk that holds a candidate
-          // (rare once the thresholds have warmed up) is parked in this lane's 128-byte row of the warp's staging tile so that
-          // the hits can be fetched by (dynamic) bit index; the hit mask is built without branches.
+          // 2 x 32 similarities of this thread's row.  Fast path: max tree per 32 values.  A chunk that holds a candidate (rare once
+          // the thresholds have warmed up) is parked in this lane's 128-byte row of the warp's staging tile so that the hits can be
+          // fetched by (dynamic) bit index; the hit mask is built without branches.  ONE atomicAdd reserves the slots of all hits of
+          // the chunk, and its result is not consumed here: up to two (column, value) pairs wait in registers and are written when
+          // the lane next has a hit or at the end of the tile, so the ~1 us atomic round trip is off the warp's critical path (with
+          // an atomic + dependent store per hit the epilogue, not the UMMAs, paced these K = 256 tiles: 17 % of the samples sat on
+          // the returned slot).
           auto chunk = [&](const uint32_t (&v)[32], int64_t nbase) {
-            float mx = __uint_as_float(v[0]);
+            // four independent 3-input max chains (5 deep) instead of one 31-deep chain
+            float c0 = __uint_as_float(v[0]), c1 = __uint_as_float(v[8]), c2 = __uint_as_float(v[16]), c3 = __uint_as_float(v[24]);
 #pragma unroll
-            for (int j = 1; j < 32; j++) mx = fmaxf(mx, __uint_as_float(v[j]));
+            for (int j = 1; j < 8; j += 2) {
+              c0 = fmaxf(fmaxf(c0, __uint_as_float(v[j])), __uint_as_float(v[j + 1 < 8 ? j + 1 : j]));
+              c1 = fmaxf(fmaxf(c1, __uint_as_float(v[8 + j])), __uint_as_float(v[8 + (j + 1 < 8 ? j + 1 : j)]));
+              c2 = fmaxf(fmaxf(c2, __uint_as_float(v[16 + j])), __uint_as_float(v[16 + (j + 1 < 8 ? j + 1 : j)]));
+              c3 = fmaxf(fmaxf(c3, __uint_as_float(v[24 + j])), __uint_as_float(v[24 + (j + 1 < 8 ? j + 1 : j)]));
+            }
+            const float mx = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
             if (mx >= flt_thr) {
               uint32_t mask = 0u;
 #pragma unroll
               for (int j = 0; j < 32; j++) mask |= (__uint_as_float(v[j]) >= flt_thr ? 1u : 0u) << j;
+              const int64_t left = p.N - nbase;                              // columns of this chunk inside the matrix
+              if (left < 32) mask &= left <= 0 ? 0u : ((1u << left) - 1u);
               const uint32_t mine = stg + (uint32_t)lane * 128;
 #pragma unroll
               for (int j = 0; j < 8; j++) sts128(mine + (uint32_t)((j ^ (lane & 7)) << 4), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-              while (mask) {
-                const int j = __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (nbase + j < p.N) {
-                  uint32_t bits;
-                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(bits) : "r"(mine + (uint32_t)((((j >> 2) ^ (lane & 7)) << 4) + (j & 3) * 4)) : "memory");
-                  const int slot = atomicAdd(p.flt.count + row, 1);
-                  if (slot < p.flt.cap) p.flt.cand[row * p.flt.cap + slot] = make_uint2((uint32_t)(p.flt.col_base + nbase + j), bits);
-                  else *p.flt.overflow = 1;
+              auto value_at = [&](int j) {
+                uint32_t bits;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(bits) : "r"(mine + (uint32_t)((((j >> 2) ^ (lane & 7)) << 4) + (j & 3) * 4)) : "memory");
+                return bits;
+              };
+              flt_flush();                                                   // the previous reservation returned long ago
+              const int n = __popc(mask);
+              if (n > 0) {
+                const int base = atomicAdd(p.flt.count + row, n);
+                if (n <= 2) {
+                  const int j0 = __ffs(mask) - 1;
+                  pend_col[0] = (uint32_t)(p.flt.col_base + nbase + j0); pend_val[0] = value_at(j0);
+                  if (n == 2) {
+                    const int j1 = 31 - __clz(mask);
+                    pend_col[1] = (uint32_t)(p.flt.col_base + nbase + j1); pend_val[1] = value_at(j1);
+                  }
+                  pend_base = base; pend_n = n;
+                } else {                                                     // many hits (the first super-block: everything passes)
+                  int slot = base;
+                  while (mask) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    if (slot < p.flt.cap) p.flt.cand[row * p.flt.cap + slot] = make_uint2((uint32_t)(p.flt.col_base + nbase + j), value_at(j));
+                    else *p.flt.overflow = 1;
+                    slot++;
+                  }
                 }
               }
             }
@@ -438,6 +485,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
 
     }
+    if constexpr (FILT) flt_flush();
   }
 
   if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // outstanding TMA stores
