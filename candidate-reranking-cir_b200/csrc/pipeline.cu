@@ -202,7 +202,7 @@ constexpr float VIT_EPS = 1e-6f;     // src/vit.py:142
 }  // namespace
 
 // ctx_s = softmax(Q K^T / 8 + mask) V of the text self-attention of `batch` streams (captions x L rows each, stream stride
-// caps*L rows in hin / qkv / ctxout), Q|K|V = hin Wqkv^T + b.  bf16 with L = 16 / 32: one fused kernel (the projection never
+// caps*L rows in hin / qkv / ctxout), Q|K|V = hin Wqkv^T + b.  bf16 with L in {8, 16, 24, 32}: one fused kernel (the projection never
 // reaches HBM); otherwise the QKV GEMM into `qkv` followed by one attention call per stream.
 static int self_attention(cir_ctx* ctx, const void* hin, const void* wqkv, const float* bqkv, int batch, const int32_t* mask,
                           const int32_t* mask_index, int64_t caps, int64_t L, void* qkv, void* ctxout) {

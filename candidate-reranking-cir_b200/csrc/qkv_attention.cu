@@ -38,7 +38,7 @@ constexpr int B_BYTES = B_ROWS * BK * 2;           // 12 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int STAGES = 6;
 constexpr int PITCH = 400;              // bytes per staged row (192 bf16 = 384 B + 16 B pad: ldmatrix / row-per-lane stores conflict-free)
-constexpr int STAGING_BYTES = BM * PITCH;
+constexpr int STAGING_BYTES = (BM + 8) * PITCH;   // + 8 rows: the 16-row fragment loads of an 8-token caption's unit run past row 127
 constexpr int BAR_BYTES = 192;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + STAGING_BYTES + BAR_BYTES + ACC_STAGES * BN * 4;
 constexpr int DH = CIR_HEAD_DIM;        // 64
@@ -85,11 +85,15 @@ __device__ __forceinline__ bool next_tile(const Params& p, int worker, int num_w
   return true;
 }
 
-// NT = key n-tiles of 8 (L / 8): 2 or 4
+// NT = key n-tiles of 8 (L / 8): 1..4.  A CTA's 128 accumulator rows hold CAPS = 128 / L whole captions (ROWS = CAPS * L rows: 128
+// for L = 8 / 16 / 32, 120 for L = 24 -- the tile then advances by 240 rows and the last 8 rows of each CTA are dead); the attention is
+// done in units of (caption, 16-query-row block), UNITS = CAPS * ceil(L / 16) of them spread over the 8 epilogue warps.
 template <int NT>
 __global__ void __launch_bounds__(THREADS, 1)
 qkv_attention_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p) {
   constexpr int L = NT * 8;
+  constexpr int CAPS = BM / L, ROWS = CAPS * L, TILE_ROWS = 2 * ROWS;
+  constexpr int MT = (L + 15) / 16, UNITS = CAPS * MT, KS = (NT + 1) / 2;
   const uint32_t rank = cluster_ctarank();
   const int worker = (int)(blockIdx.x >> 1);
   const int num_workers = (int)(gridDim.x >> 1);
@@ -133,7 +137,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       int stage = 0; uint32_t phase = 0;
       int b, m_blk, h;
       for (int it = 0; next_tile(p, worker, num_workers, it, b, m_blk, h); ++it) {
-        const int32_t a_row = (int32_t)(b * p.a_rows_per_batch + (int64_t)m_blk * (2 * BM) + rank * BM);
+        const int32_t a_row = (int32_t)(b * p.a_rows_per_batch + (int64_t)m_blk * TILE_ROWS + rank * ROWS);
         int32_t w_row[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
@@ -195,6 +199,8 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int etid = threadIdx.x - 64;
     const int g = lane >> 2, t = lane & 3;
     const float sl2 = p.scale * 1.4426950408889634f;
+    // the 8 pad rows behind the staged tile are only ever READ (fragment loads that run past row 127 and meet probability 0): keep them finite
+    if (etid < 8 * PITCH / 16) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(stg + (uint32_t)(BM * PITCH) + (uint32_t)etid * 16), "r"(0u) : "memory");
     int acc = 0; uint32_t acc_phase = 0;
     int b, m_blk, h;
     for (int it = 0; next_tile(p, worker, num_workers, it, b, m_blk, h); ++it) {
@@ -238,21 +244,26 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       asm volatile("bar.sync 2, 256;" ::: "memory");             // the 128 x 192 tile is staged
-      // ---- attention of query rows [16 ew, 16 ew + 16): one caption (L is a multiple of 16), keys = its L rows
-      const int64_t row_lo = (int64_t)m_blk * (2 * BM) + rank * BM + ew * 16;       // row within the batch
-      if (row_lo >= p.M) continue;                               // tail tile: rows beyond the batch (warp-uniform)
-      const int64_t cap = row_lo / L;                            // caption (= triplet) index within the batch
-      const int krow0 = (ew * 16 / L) * L;                       // first staged row of the caption
+      // ---- attention, one unit = 16 query rows of one caption against the caption's L keys
+      const int64_t tile_row0 = (int64_t)m_blk * TILE_ROWS + rank * ROWS;            // first row of this CTA's captions within the batch
+      auto unit = [&](const int u) {
+      const int cl = u / MT, mt = u - cl * MT;                   // caption within the CTA, 16-row block within the caption
+      const int krow0 = cl * L, qrow0 = krow0 + mt * 16;         // staged rows of the caption's keys / of this unit's queries
+      const int64_t row_lo = tile_row0 + qrow0;                  // row within the batch
+      if (tile_row0 + krow0 >= p.M) return;                      // tail tile: captions beyond the batch (warp-uniform)
+      const int nvalid = (L % 16 == 0) ? 16 : (L - mt * 16 < 16 ? L - mt * 16 : 16);    // 16, or 8 in the last block of a 24- / 8-token caption
+      const int64_t cap = (tile_row0 + krow0) / L;               // caption (= triplet) index within the batch
       const int32_t* mask = p.key_mask ? p.key_mask + (int64_t)(p.mask_index ? __ldg(p.mask_index + cap) : cap) * L : nullptr;
       float madd[NT][2];
 #pragma unroll
       for (int j = 0; j < NT; j++)
 #pragma unroll
         for (int e = 0; e < 2; e++) madd[j][e] = (mask && __ldg(mask + j * 8 + 2 * t + e) == 0) ? -10000.0f * 1.4426950408889634f : 0.f;
-      // Q fragments (A operand, 16 rows x 64): matrix i of an x4 load = rows (i&1)*8.., columns (i>>1)*8..
+      // Q fragments (A operand, 16 rows x 64): matrix i of an x4 load = rows (i&1)*8.., columns (i>>1)*8..  (rows past the caption
+      // belong to the next one or are dead: their results are never stored)
       uint32_t qa[4][4];
       {
-        const uint32_t qaddr = stg + (uint32_t)(ew * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (uint32_t)((lane >> 4) * 8) * 2;
+        const uint32_t qaddr = stg + (uint32_t)(qrow0 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (uint32_t)((lane >> 4) * 8) * 2;
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) ldmatrix_x4(qaddr + (uint32_t)(kk * 16) * 2, qa[kk]);
       }
@@ -284,7 +295,9 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
       m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
       float l0 = 0.f, l1 = 0.f;
-      uint32_t pa[NT / 2][4];
+      uint32_t pa[KS][4];
+#pragma unroll
+      for (int j = 0; j < KS; j++) { pa[j][0] = pa[j][1] = pa[j][2] = pa[j][3] = 0u; }      // keys past L (odd NT) carry probability 0
 #pragma unroll
       for (int j = 0; j < NT; j++) {
         const float p00 = exp2f(sc[j][0] - m0), p01 = exp2f(sc[j][1] - m0);
@@ -295,12 +308,12 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
       l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
       l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      // O = P V: V rows are keys (k), columns head dims (n) -> transposed ldmatrix
+      // O = P V: V rows are keys (k), columns head dims (n) -> transposed ldmatrix (rows past L meet probability 0)
       float o[8][4];
 #pragma unroll
       for (int j = 0; j < 8; j++) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
 #pragma unroll
-      for (int kk = 0; kk < NT / 2; kk++) {
+      for (int kk = 0; kk < KS; kk++) {
         const int vrow = krow0 + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
         const uint32_t vaddr = stg + (uint32_t)vrow * PITCH + (uint32_t)(2 * DH + (lane >> 4) * 8) * 2;
 #pragma unroll
@@ -312,14 +325,15 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
       }
       const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-      // context rows over this warp's own Q rows (nobody else reads them), then out as whole 128-byte row segments
+      // context rows over this unit's own (valid) Q rows -- nobody else reads them --, then out as whole 128-byte row segments
       __syncwarp();
       {
-        const uint32_t o0 = stg + (uint32_t)(ew * 16 + g) * PITCH + (uint32_t)(2 * t) * 2;
+        const uint32_t o0 = stg + (uint32_t)(qrow0 + g) * PITCH + (uint32_t)(2 * t) * 2;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(o0 + (uint32_t)(j * 8) * 2), "r"(pack_bf16(o[j][0] * i0, o[j][1] * i0)) : "memory");
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(o0 + 8u * PITCH + (uint32_t)(j * 8) * 2), "r"(pack_bf16(o[j][2] * i1, o[j][3] * i1)) : "memory");
+          if (nvalid == 16)
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(o0 + 8u * PITCH + (uint32_t)(j * 8) * 2), "r"(pack_bf16(o[j][2] * i1, o[j][3] * i1)) : "memory");
         }
       }
       __syncwarp();
@@ -328,11 +342,21 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           const int r = i * 4 + (lane >> 3);
-          uint4 v;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                       : "r"(stg + (uint32_t)(ew * 16 + r) * PITCH + (uint32_t)(lane & 7) * 16) : "memory");
-          *reinterpret_cast<uint4*>(op + (row_lo + r) * p.out_rs) = v;
+          if (r < nvalid) {
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(stg + (uint32_t)(qrow0 + r) * PITCH + (uint32_t)(lane & 7) * 16) : "memory");
+            *reinterpret_cast<uint4*>(op + (row_lo + r) * p.out_rs) = v;
+          }
         }
+      }
+      __syncwarp();
+      };
+      if constexpr (UNITS == NUM_EPI_WARPS) {
+        unit(ew);                                                // L = 16 / 32: exactly one unit per warp
+      } else {
+#pragma unroll 1
+        for (int u = ew; u < UNITS; u += NUM_EPI_WARPS) unit(u);
       }
     }
   }
@@ -348,7 +372,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
 template <int NT>
 static int launch(cir_ctx* ctx, const Params& p, const CUtensorMap& ma, const CUtensorMap& mw, double work) {
-  const unsigned bit = 1u << (24 + (NT == 4 ? 0 : 1));
+  const unsigned bit = NT == 4 ? 1u << 24 : (NT == 2 ? 1u << 25 : (NT == 3 ? 1u << 30 : 1u << 31));
   if (!(ctx->func_attr_mask & bit)) {
     CIR_CUDA(cudaFuncSetAttribute(qkv_attention_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     ctx->func_attr_mask |= bit;
@@ -378,14 +402,14 @@ static int launch(cir_ctx* ctx, const Params& p, const CUtensorMap& ma, const CU
 }  // namespace qkvattn
 
 bool cir_qkv_attention_supported(const cir_ctx* ctx, int64_t L) {
-  return ctx->dtype == CIR_DTYPE_BF16 && ctx->gemm_impl != CIR_GEMM_SIMT && ctx->attn_impl == 0 && ctx->gemm_pair && (L == 16 || L == 32);
+  return ctx->dtype == CIR_DTYPE_BF16 && ctx->gemm_impl != CIR_GEMM_SIMT && ctx->attn_impl == 0 && ctx->gemm_pair && (L == 8 || L == 16 || L == 24 || L == 32);
 }
 
 extern "C" int cir_qkv_attention(cir_ctx* ctx, const cir_qkv_attn_args* a) {
   CIR_ENTER(ctx);
   CIR_CHECK_ARG(a && a->x && a->w && a->out, "qkv_attention: null operand");
   if (a->captions == 0 || a->batch == 0) return CIR_OK;
-  CIR_CHECK_ARG(cir_qkv_attention_supported(ctx, a->L), "qkv_attention: needs a bf16 tcgen05 context and L = 16 or 32 (got L=%d)", a->L);
+  CIR_CHECK_ARG(cir_qkv_attention_supported(ctx, a->L), "qkv_attention: needs a bf16 tcgen05 context and L in {8, 16, 24, 32} (got L=%d)", a->L);
   CIR_CHECK_ARG(a->batch >= 1 && a->captions > 0, "qkv_attention: bad shape");
   CIR_CHECK_ARG(((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->w & 15) == 0 && ((uintptr_t)a->out & 15) == 0 && (a->out_rs % 8) == 0 &&
                 (a->out_bs % 8) == 0, "qkv_attention: operands must be 16 B aligned");
@@ -401,7 +425,8 @@ extern "C" int cir_qkv_attention(cir_ctx* ctx, const cir_qkv_attn_args* a) {
   const int64_t a_rows = p.a_rows_per_batch * (a->batch - 1) + p.M;
   const int64_t w_rows = (int64_t)3 * DM * a->batch;
   CIR_CHECK_ARG(a_rows < (1ll << 31), "qkv_attention: too many rows for a 32-bit TMA coordinate");
-  p.m_blocks = (int32_t)((p.M + 2 * BM - 1) / (2 * BM));
+  const int64_t tile_rows = 2 * (BM / a->L) * a->L;           // 256, or 240 for L = 24
+  p.m_blocks = (int32_t)((p.M + tile_rows - 1) / tile_rows);
   p.k_blocks = DM / BK;
   const int64_t nt = (int64_t)p.m_blocks * HEADS * a->batch;
   CIR_CHECK_ARG(nt < (1ll << 31), "qkv_attention: too many tiles");
@@ -411,5 +436,10 @@ extern "C" int cir_qkv_attention(cir_ctx* ctx, const cir_qkv_attn_args* a) {
   CIR_TRY(cir_make_map_2d(ctx, &ma, a->x, a_rows, DM, DM, BM));
   CIR_TRY(cir_make_map_2d(ctx, &mw, a->w, w_rows, DM, DM, SLAB_ROWS));
   const double work = 2.0 * (double)p.M * 3.0 * DM * DM * a->batch + 4.0 * (double)a->captions * a->batch * HEADS * (double)a->L * a->L * DH;
-  return a->L == 32 ? launch<4>(ctx, p, ma, mw, work) : launch<2>(ctx, p, ma, mw, work);
+  switch (a->L) {
+    case 32: return launch<4>(ctx, p, ma, mw, work);
+    case 24: return launch<3>(ctx, p, ma, mw, work);
+    case 16: return launch<2>(ctx, p, ma, mw, work);
+    default: return launch<1>(ctx, p, ma, mw, work);
+  }
 }

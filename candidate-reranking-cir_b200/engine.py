@@ -69,7 +69,7 @@ class Engine:
         N.check(self._lib.cir_set_dedup_first_layer(self.ctx, 1 if enable else 0))
 
     def set_fuse_qkv_attention(self, enable: bool):
-        """bf16, L = 16 / 32: QKV projection + masked text self-attention as one kernel (default on; bit-equal to the unfused path)."""
+        """bf16, L in {8, 16, 24, 32}: QKV projection + masked text self-attention as one kernel (default on; bit-equal to the unfused path)."""
         N.check(self._lib.cir_set_fuse_qkv_attention(self.ctx, 1 if enable else 0))
 
     def set_stage1_tensor_cores(self, enable: bool):

@@ -76,7 +76,7 @@ int  cir_set_prune_last_layer(cir_ctx* ctx, int enable);
 /* stage II: layer 0's self-attention block and cross query projection depend on the query only (both streams are expanded
  * copies, src/blip_stage2.py:118-124): run them once per unique query of a chunk and expand (default on; exact) */
 int  cir_set_dedup_first_layer(cir_ctx* ctx, int enable);
-/* bf16 mode, captions of 16 or 32 tokens: the query/key/value Linears and the masked text self-attention run as ONE kernel
+/* bf16 mode, captions of 8, 16, 24 or 32 tokens: the query/key/value Linears and the masked text self-attention run as ONE kernel
  * (cir_qkv_attention) -- the [rows, 2304] projection never reaches HBM.  Default on; 0 = GEMM + attention kernel (bit-equal). */
 int  cir_set_fuse_qkv_attention(cir_ctx* ctx, int enable);
 /* bf16 contexts, galleries of >= 16,384 rows: cir_stage1_topk computes the similarities on the tensor cores (bf16 operands) only to
@@ -163,7 +163,7 @@ int cir_attention(cir_ctx* ctx, const cir_attn_args* args);
 /* Fused self-attention block input side: out[b][c*L + l, h*64 + d] = softmax(Q_h K_h^T * scale + mask) V_h with
  * [Q|K|V] = x[b] w[b]^T + bias[b] (query / key / value Linears stacked as [2304, 768], PyTorch [out, in] layout);
  * replaces BertSelfAttention.forward for text self-attention (src/nlvr_encoder.py:140-222, src/med.py:112-216).
- * bf16 context only; L in {16, 32}; rows of x / out are caption-major (row = caption*L + token), row stride 768 / out_rs.
+ * bf16 context only; L in {8, 16, 24, 32}; rows of x / out are caption-major (row = caption*L + token), row stride 768 / out_rs.
  * key_mask int32 [*, L] (1 = attend, 0 -> additive -10000), row mask_index[c] (NULL: c) belongs to caption c. */
 typedef struct cir_qkv_attn_args {
   const void* x; int64_t x_bs;          /* [batch][captions*L, 768] bf16; batch stride in elements */
