@@ -135,6 +135,30 @@ topk_rows_kernel(TopkParams p) {
   }
 }
 
+// Merge of P per-shard lists in ONE pass: the P*K composite keys of a query (<= 8192) are sorted once in shared memory and the first K
+// leave.  Keys are unique across shards (disjoint global indices), so the result equals the sequential merge bit for bit.
+__global__ void __launch_bounds__(THREADS)
+merge_lists_kernel(const float* __restrict__ dist_in, const int32_t* __restrict__ idx_in, int P, int64_t Q, int K, int n_pad,
+                   float* __restrict__ out_dist, int32_t* __restrict__ out_idx) {
+  extern __shared__ uint64_t skeys[];
+  const int64_t q = blockIdx.x;
+  for (int i = threadIdx.x; i < n_pad; i += THREADS) {
+    uint64_t key = KEY_MAX;
+    if (i < P * K) {
+      const int s = i / K, j = i - s * K;
+      const int32_t gi = idx_in[((int64_t)s * Q + q) * K + j];
+      if (gi >= 0) key = ((uint64_t)ordered_bits(dist_in[((int64_t)s * Q + q) * K + j]) << 32) | (uint32_t)gi;   // -1: empty slot of a short shard
+    }
+    skeys[i] = key;
+  }
+  bitonic_sort(skeys, n_pad);
+  for (int i = threadIdx.x; i < K; i += THREADS) {
+    const uint64_t key = skeys[i];
+    out_idx[q * K + i] = (key == KEY_MAX) ? -1 : (int32_t)(key & 0xFFFFFFFFu);
+    out_dist[q * K + i] = (key == KEY_MAX) ? INFINITY : from_ordered_bits((uint32_t)(key >> 32));
+  }
+}
+
 struct RecallParams { int32_t ks[16]; int32_t num; };
 __global__ void recall_counts_kernel(const uint8_t* __restrict__ labels, const int32_t* __restrict__ order, int64_t Q, int64_t K,
                                      RecallParams rp, unsigned long long* __restrict__ hits) {
@@ -304,6 +328,16 @@ extern "C" int cir_topk_merge(cir_ctx* ctx, const float* dist_in, const int32_t*
   if (Q == 0 || P == 0) return CIR_OK;
   CIR_CHECK_ARG(K >= 1 && K <= MAXK, "topk_merge: K=%lld out of range", (long long)K);
   if (workspace_bytes < cir_topk_workspace_bytes(Q, 0, K)) { cir_set_error("topk_merge: workspace too small"); return CIR_EWORKSPACE; }
+  if (P * K <= 8192) {                                   // all lists of a query fit one shared-memory sort: a single launch
+    const int n_pad = pow2_at_least(P * K);
+    if (!(ctx->func_attr_mask & (1u << 7))) {
+      CIR_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+      ctx->func_attr_mask |= 1u << 7;
+    }
+    merge_lists_kernel<<<(unsigned)Q, THREADS, (size_t)n_pad * 8, ctx->stream>>>(dist_in, idx_in, (int)P, Q, (int)K, n_pad, top_dist, top_idx);
+    CIR_LAUNCH_CHECK(ctx);
+    return CIR_OK;
+  }
   uint64_t* scratch = (uint64_t*)workspace;
   for (int64_t s = 0; s < P; s++) {
     TopkParams p{};

@@ -93,11 +93,11 @@ def sharded_stage1_topk(local_topk_fn: Callable[[slice], Tuple[torch.Tensor, tor
     d, i = local_topk_fn(rows)
     if ws == 1:
         return d, i
-    ds = [torch.empty_like(d) for _ in range(ws)]
-    is_ = [torch.empty_like(i) for _ in range(ws)]
-    dist.all_gather(ds, d.contiguous())
-    dist.all_gather(is_, i.contiguous())
-    return merge_fn(torch.stack(ds), torch.stack(is_))
+    ds = torch.empty((ws,) + tuple(d.shape), dtype=d.dtype, device=d.device)          # gathered straight into [P, Q, K]
+    is_ = torch.empty((ws,) + tuple(i.shape), dtype=i.dtype, device=i.device)
+    dist.all_gather_into_tensor(ds.view(-1, *d.shape[1:]), d.contiguous())            # (concatenation along dim 0: what gloo accepts too)
+    dist.all_gather_into_tensor(is_.view(-1, *i.shape[1:]), i.contiguous())
+    return merge_fn(ds, is_)
 
 
 # ---- engine-backed convenience wrappers (GPU) ---------------------------------------------------------------
