@@ -158,3 +158,77 @@ if __name__ == "__main__":
         qkv_probe()
     if "stage2_profile" in which:      # one short pass for an ncu launch list
         stage2_probe(reps=1, configs=((4096, 64),), Q=int(os.environ.get("CIR_PROBE_Q", "96")))
+
+
+def power_probe(seconds=4.0):
+    """Which kernels run into the board's power cap?  Each kernel class of the stage-II step is looped alone for a few seconds while
+    nvidia-smi samples SM clock and power draw."""
+    import subprocess, threading
+    T, L, C = 4096, 32, 46
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, T, L, 768, generator=g).cuda().bfloat16()
+    w = (torch.randn(2, 2304, 768, generator=g) * 0.04).cuda().bfloat16()
+    bias = torch.randn(2, 2304, generator=g).cuda()
+    mask = torch.ones(T, L, dtype=torch.int32).cuda()
+    A = torch.randn(2 * T * L, 768, device="cuda").bfloat16()
+    W1 = (torch.randn(3072, 768, device="cuda") * 0.04).bfloat16()
+    gam, bet = torch.ones(768, device="cuda"), torch.zeros(768, device="cuda")
+    slot = torch.sort(torch.arange(T) % C).values.int()
+    q = torch.randn(T, L, 768, device="cuda").bfloat16()
+    kv = torch.randn(C, 577, 3072, device="cuda").bfloat16()
+    o = torch.empty(T, L, 1536, device="cuda", dtype=torch.bfloat16)
+    import ctypes as C_
+    tiles = e._i32(cir.schedule.build_attn_tiles(slot.numpy(), L))
+    slot_d = slot.cuda()
+
+    def attn():
+        a = N_.AttnArgs()
+        a.q, a.k, a.v, a.o = N_.ptr(q), N_.ptr(kv), N_.vp(kv.data_ptr() + 768 * 2), N_.ptr(o)
+        a.q_bs, a.q_rs = L * 768, 768
+        a.k_bs = a.v_bs = 577 * 3072
+        a.k_rs = a.v_rs = 3072
+        a.o_bs, a.o_rs = L * 1536, 1536
+        a.kv_index = N_.ptr(slot_d)
+        a.key_mask = a.mask_index = N_.vp(0)
+        a.work, a.num_work = N_.vp(0), 0
+        a.tiles, a.num_tiles = N_.ptr(tiles), tiles.shape[0]
+        a.kv_batches = C
+        a.B, a.H, a.Lq, a.Lk, a.scale = T, 12, L, 577, 0.125
+        e._sync_stream()
+        N_.check(e._lib.cir_attention(e.ctx, C_.byref(a)))
+    kernels = {"gemm FFN1 (262144 x 3072 x 768)": lambda: e.gemm(A, W1, None, act=1),
+               "fused QKV + self-attention": lambda: e.qkv_attention(x, w, bias, key_mask=mask),
+               "tcgen05 cross-attention": attn,
+               "LayerNorm (262144 rows)": lambda: e.add_layernorm(A, gam, bet)}
+    for name, fn in kernels.items():
+        rows, stop = [], [False]
+
+        def sample():
+            while not stop[0]:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-i", "0"],
+                                     capture_output=True, text=True).stdout.strip()
+                if out:
+                    rows.append([c.strip() for c in out.split(",")])
+                time.sleep(0.1)
+        th = threading.Thread(target=sample, daemon=True)
+        fn(); torch.cuda.synchronize()
+        th.start()
+        t0 = time.time(); n = 0
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        while time.time() - t0 < seconds:
+            for _ in range(20):
+                fn()
+            n += 20
+            torch.cuda.synchronize()
+        t.record(); torch.cuda.synchronize()
+        stop[0] = True; th.join()
+        rows = rows[len(rows) // 3:]                         # steady state
+        clk = sorted(int(r[0]) for r in rows)[len(rows) // 2] if rows else -1
+        pw = sorted(float(r[1]) for r in rows)[len(rows) // 2] if rows else -1
+        cap = sum(r[2].lower().startswith("active") for r in rows) / max(1, len(rows))
+        print(f"{name:40s} {s.elapsed_time(t) / n:.3f} ms/launch  SM clock {clk} MHz  power {pw:.0f} W  sw_power_cap active in {100 * cap:.0f} % of samples", flush=True)
+
+
+if "power" in sys.argv[1:]:
+    power_probe()

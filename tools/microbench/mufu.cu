@@ -14,6 +14,9 @@ template <int MODE> __global__ void k(float* out, int iters) {
       if (MODE == 2) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(h[i]));
       if (MODE == 3) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[i]));
       if (MODE == 4) asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(h[i]));
+      if (MODE == 5) { asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(a[i]), "f"(a[(i + 1) & 7])); a[i] += __uint_as_float(h[i]); }   // pack + one FADD to keep a dependency
+      if (MODE == 6) { a[i] += a[(i + 1) & 7]; }                                                                                              // the FADD alone
+      if (MODE == 7) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(a[i]), "f"(a[(i + 1) & 7])); }   // ex2 + pack per element
     }
   }
   float s = 0; for (int i = 0; i < 8; i++) s += a[i] + __uint_as_float(h[i]);
@@ -32,5 +35,6 @@ template <int MODE> void run(const char* name, int per) {
 int main() {
   run<0>("ex2.approx.ftz.f32", 1); run<1>("ex2.approx.f16x2", 2); run<2>("ex2.approx.ftz.bf16x2", 2);
   run<3>("tanh.approx.f32", 1); run<4>("tanh.approx.bf16x2", 2);
+  run<5>("cvt.rn.bf16x2.f32 + fadd", 1); run<6>("fadd alone", 1); run<7>("ex2 + cvt.rn.bf16x2 per elem", 1);
   return 0;
 }
