@@ -65,6 +65,24 @@ __device__ __forceinline__ float ex2_approx(float x) {       // one MUFU.EX2; ex
   return r;
 }
 
+// packed fp32 pairs (FFMA2 / FADD2 on sm_100: one issue slot for two IEEE fp32 operations)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // O[row, 0:64] *= alpha in TMEM (whole warp, each lane its own row/alpha); rare path, kept out of line
 __device__ __noinline__ void rescale_o(uint32_t o_addr, float alpha) {
 #pragma unroll
@@ -331,23 +349,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         //      Two instantiations: full chunks carry no per-element masking; the tail chunk zero-fills the padded keys.
         auto exp_pack = [&](auto full_tag) {
           constexpr bool FULL = decltype(full_tag)::value;
+          const uint64_t sl2_2 = pack_f32x2(sl2, sl2), negm_2 = pack_f32x2(-m, -m);
+          uint64_t lsum = pack_f32x2(0.f, 0.f);              // two partial row sums (even / odd keys)
 #pragma unroll
           for (int c = 0; c < 8; c++) {
             float e[8];
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
+            for (int q = 0; q < 8; q += 2) {
               const int x = c * 8 + q;
-              const float sv = __uint_as_float(x < 32 ? v0[x & 31] : v1[x & 31]);
-              e[q] = ex2_approx(fmaf(sv, sl2, -m));
+              const uint32_t s0 = x < 32 ? v0[x & 31] : v1[x & 31], s1 = x < 32 ? v0[(x + 1) & 31] : v1[(x + 1) & 31];
+              float a0, a1;
+              unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s0), __uint_as_float(s1)), sl2_2, negm_2), a0, a1);   // one FFMA2 per key pair
+              e[q] = ex2_approx(a0);
+              e[q + 1] = ex2_approx(a1);
               if (!FULL && x >= keys) e[q] = 0.f;
+              if (!FULL && x + 1 >= keys) e[q + 1] = 0.f;
             }
-            l += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+            lsum = add_f32x2(lsum, add_f32x2(add_f32x2(pack_f32x2(e[0], e[1]), pack_f32x2(e[2], e[3])),
+                                             add_f32x2(pack_f32x2(e[4], e[5]), pack_f32x2(e[6], e[7]))));
 #pragma unroll
             for (int q = 0; q < 4; q++) {
               const __nv_bfloat162 h2 = __floats2bfloat162_rn(e[2 * q], e[2 * q + 1]);
               v0[c * 4 + q] = *reinterpret_cast<const uint32_t*>(&h2);       // in place: scores 8c.. of v0 / v1 are consumed by now
             }
           }
+          float la, lb;
+          unpack_f32x2(lsum, la, lb);
+          l += la + lb;
         };
         if (t == 1 || g > 0) turn_wait();
         if (full_chunk) exp_pack(std::true_type{}); else exp_pack(std::false_type{});
