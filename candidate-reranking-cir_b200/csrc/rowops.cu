@@ -69,6 +69,14 @@ __device__ __forceinline__ void layernorm24(float (&v)[PER_LANE], const float* g
   for (int i = 0; i < PER_LANE; i++) v[i] = fmaf((v[i] - mean) * rstd, g[i], b[i]);
 }
 
+// packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo2(uint64_t v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(uint64_t v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 // The raw 24 elements of one row held by this lane, loaded now and unpacked later (so that the next row's loads are in
 // flight while the current row is reduced).
 template <typename T> struct RawRow;
@@ -117,10 +125,17 @@ add_layernorm_kernel(const TX* __restrict__ x, int64_t x_rows, const TR* __restr
   const int n = (int)(rows - r0 < LN_ROWS ? rows - r0 : LN_ROWS);
   RawRow<TX> xr;
   RawRow<TR> rr;
-  xr.load(x + (r0 % x_rows) * D, lane);
+  // row -> x row (r % x_rows) and parameter group (r / rows_per_group) advance incrementally: one 64-bit division each per warp,
+  // not per row (a 64-bit divide is ~100 instructions; two per row were a third of the kernel's instruction stream)
+  // (32-bit: the launcher guarantees rows < 2^31; the common cases -- no broadcast, one group -- need no division at all)
+  const uint32_t r32 = (uint32_t)r0;
+  int64_t xi = (uint64_t)x_rows > (uint64_t)r0 ? r0 : (int64_t)(r32 % (uint32_t)x_rows);
+  int64_t gr = (uint64_t)rows_per_group > (uint64_t)r0 ? 0 : (int64_t)(r32 / (uint32_t)rows_per_group);
+  int64_t gleft = (gr + 1) * rows_per_group - r0;            // rows left in the current group, this one included
+  xr.load(x + xi * D, lane);
   if (res) rr.load(res + r0 * D, lane);
   float g[PER_LANE], b[PER_LANE];
-  int64_t grp = -1;
+  bool fresh = true;                                          // gamma / beta must be (re)loaded
 #pragma unroll 1
   for (int i = 0; i < n; i++) {
     const int64_t r = r0 + i;
@@ -133,25 +148,37 @@ add_layernorm_kernel(const TX* __restrict__ x, int64_t x_rows, const TR* __restr
       for (int k = 0; k < PER_LANE; k++) v[k] += t[k];
     }
     if (i + 1 < n) {                                          // next row's reads go out before this row's reductions
-      xr.load(x + ((r + 1) % x_rows) * D, lane);
+      xi = xi + 1 == x_rows ? 0 : xi + 1;
+      xr.load(x + xi * D, lane);
       if (res) rr.load(res + (r + 1) * D, lane);
     }
-    const int64_t gr = r / rows_per_group;
-    if (gr != grp) {                                          // warp-uniform
-      grp = gr;
+    if (fresh) {                                              // warp-uniform
+      fresh = false;
       load_row<float>(gamma + gr * D, lane, g);
       load_row<float>(beta + gr * D, lane, b);
     }
-    float s = 0.f;
+    if (--gleft == 0) { gr++; gleft = rows_per_group; fresh = true; }
+    // statistics and normalisation on packed fp32 pairs (FADD2 / FFMA2 / FMUL2: one issue slot for two IEEE fp32 operations; the
+    // kernel is paced by its ~280 instructions per row at 16 warps per SM, not by HBM -- profiles/r02_layernorm_selfattn_full.txt);
+    // per-element arithmetic is unchanged, the row sums are two interleaved partial sums
+    uint64_t v2[PER_LANE / 2];
 #pragma unroll
-    for (int k = 0; k < PER_LANE; k++) s += v[k];
-    const float mean = warp_sum(s) * (1.0f / D);
-    float q = 0.f;
+    for (int k = 0; k < PER_LANE / 2; k++) v2[k] = pk2(v[2 * k], v[2 * k + 1]);
+    uint64_t s2 = pk2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < PER_LANE; k++) { float d = v[k] - mean; q = fmaf(d, d, q); }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    for (int k = 0; k < PER_LANE / 2; k++) s2 = add2(s2, v2[k]);
+    const float mean = warp_sum(lo2(s2) + hi2(s2)) * (1.0f / D);
+    const uint64_t nmean2 = pk2(-mean, -mean);
+    uint64_t q2 = pk2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < PER_LANE; k++) v[k] = fmaf((v[k] - mean) * rstd, g[k], b[k]);
+    for (int k = 0; k < PER_LANE / 2; k++) { v2[k] = add2(v2[k], nmean2); q2 = fma2(v2[k], v2[k], q2); }
+    const float rstd = rsqrtf(warp_sum(lo2(q2) + hi2(q2)) * (1.0f / D) + eps);
+    const uint64_t rstd2 = pk2(rstd, rstd);
+#pragma unroll
+    for (int k = 0; k < PER_LANE / 2; k++) {
+      const uint64_t o2 = fma2(mul2(v2[k], rstd2), pk2(g[2 * k], g[2 * k + 1]), pk2(b[2 * k], b[2 * k + 1]));
+      v[2 * k] = lo2(o2); v[2 * k + 1] = hi2(o2);
+    }
     store_row<TY>(y + r * D, lane, v);
   }
 }
@@ -278,6 +305,7 @@ extern "C" int cir_add_layernorm(cir_ctx* ctx, const void* x, int x_f32, int64_t
   CIR_ENTER(ctx);
   if (rows == 0) return CIR_OK;
   CIR_CHECK_ARG(x && gamma && beta && y && x_rows > 0 && rows_per_group > 0, "add_layernorm: null/zero argument");
+  CIR_CHECK_ARG(rows < (1ll << 31), "add_layernorm: rows=%lld does not fit 32-bit row arithmetic", (long long)rows);
   const bool f32 = ctx->dtype == CIR_DTYPE_F32;
   dim3 grid(row_blocks((rows + LN_ROWS - 1) / LN_ROWS)), block(WARPS * 32);
   {
