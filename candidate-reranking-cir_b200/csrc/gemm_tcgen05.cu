@@ -83,6 +83,25 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(hx, t, hx);
 }
 
+// packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2: one issue slot for two IEEE fp32 operations) for the epilogue math: the GEMMs run
+// at the board's power cap, so every instruction the eight epilogue warps do not issue is energy for the tensor pipe
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// gelu_fast on a pair: identical per-element arithmetic, five of the six FMA-pipe operations packed
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  const uint64_t x = pk2(x0, x1);
+  const uint64_t u = mul2(x, fma2(pk2(0.0356774081f, 0.0356774081f), mul2(x, x), pk2(0.7978845608f, 0.7978845608f)));
+  float u0, u1, t0, t1;
+  upk2(u, u0, u1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  const uint64_t hx = mul2(pk2(0.5f, 0.5f), x);
+  upk2(fma2(hx, pk2(t0, t1), hx), x0, x1);
+}
+
 // ----------------------------------------------------------------------------- the kernel
 template <int BN, bool PAIR, bool FILT>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -349,15 +368,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b0 = sb[j >> 2], b1 = sb[8 + (j >> 2)];
-            f[j] = __uint_as_float(v0[j]) + b0.x; f[j + 1] = __uint_as_float(v0[j + 1]) + b0.y;
-            f[j + 2] = __uint_as_float(v0[j + 2]) + b0.z; f[j + 3] = __uint_as_float(v0[j + 3]) + b0.w;
-            f[32 + j] = __uint_as_float(v1[j]) + b1.x; f[32 + j + 1] = __uint_as_float(v1[j + 1]) + b1.y;
-            f[32 + j + 2] = __uint_as_float(v1[j + 2]) + b1.z; f[32 + j + 3] = __uint_as_float(v1[j + 3]) + b1.w;
+            upk2(add2(pk2(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1])), pk2(b0.x, b0.y)), f[j], f[j + 1]);
+            upk2(add2(pk2(__uint_as_float(v0[j + 2]), __uint_as_float(v0[j + 3])), pk2(b0.z, b0.w)), f[j + 2], f[j + 3]);
+            upk2(add2(pk2(__uint_as_float(v1[j]), __uint_as_float(v1[j + 1])), pk2(b1.x, b1.y)), f[32 + j], f[32 + j + 1]);
+            upk2(add2(pk2(__uint_as_float(v1[j + 2]), __uint_as_float(v1[j + 3])), pk2(b1.z, b1.w)), f[32 + j + 2], f[32 + j + 3]);
           }
         }
         if (p.act == CIR_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 64; j++) f[j] = gelu_fast(f[j]);
+          for (int j = 0; j < 64; j += 2) gelu_fast2(f[j], f[j + 1]);
         } else if (p.act == CIR_ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 64; j++) f[j] = fmaxf(f[j], 0.f);
@@ -379,7 +398,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
               for (int q = 0; q < 4; q++) {
                 const float2 t = __bfloat1622float2(h2[q]);
-                f[j * 8 + 2 * q] += t.x; f[j * 8 + 2 * q + 1] += t.y;
+                upk2(add2(pk2(f[j * 8 + 2 * q], f[j * 8 + 2 * q + 1]), pk2(t.x, t.y)), f[j * 8 + 2 * q], f[j * 8 + 2 * q + 1]);
               }
             }
             __syncwarp();
