@@ -94,6 +94,16 @@ def _worker(rank, ws, port, ret):
         both = [torch.zeros_like(mine) for _ in range(ws)]
         dist.all_gather(both, mine)
         assert int((both[0] * both[1]).sum()) == 0 and int((both[0] + both[1]).sum()) == len(set(cand[active].reshape(-1).tolist()))
+        # ---- the name -> gallery-row join of the stage-II drivers, split over the ranks (uneven: 9 query rows over 2 ranks)
+        V2 = cir.validate_stage2
+        names = [f"img{i:04d}" for i in range(Gc)]
+        mat = np.array(names)[np.stack([rng.permutation(Gc)[:Kc] for _ in range(9)])]
+
+        class _Eng:
+            device = torch.device("cpu")
+        n2i = {n: i for i, n in enumerate(names)}
+        got_rows = V2._names_to_rows_sharded(_Eng(), names, n2i, mat)
+        assert np.array_equal(got_rows, V2._names_to_rows(names, n2i, mat)) and got_rows.dtype == np.int32
         ret[rank] = "ok"
     except Exception as e:  # pragma: no cover
         ret[rank] = f"{type(e).__name__}: {e}"
