@@ -431,7 +431,9 @@ extern "C" int cir_qkv_attention(cir_ctx* ctx, const cir_qkv_attn_args* a) {
   const int64_t nt = (int64_t)p.m_blocks * HEADS * a->batch;
   CIR_CHECK_ARG(nt < (1ll << 31), "qkv_attention: too many tiles");
   p.num_tiles = (int32_t)nt;
-  { const char* d = getenv("CIR_QKV_DRAIN"); p.drain = d ? atoi(d) : p.k_blocks / 2; }     // measured: 0.812 ms (never) / 0.752 (mid-tile) / 0.767 (every 4) / 0.998 (every k-block)
+  // UMMA-queue drain period in k-blocks (see the MMA warp): mid-tile by default; CIR_QKV_DRAIN overrides it for A/B measurements
+  // (sustained: 0 = never 0.960 ms, 6 = mid-tile 0.885, 4 -> 0.901; every k-block 0.998 cold)
+  { const char* d = getenv("CIR_QKV_DRAIN"); p.drain = d ? atoi(d) : p.k_blocks / 2; }
   CUtensorMap ma, mw;
   CIR_TRY(cir_make_map_2d(ctx, &ma, a->x, a_rows, DM, DM, BM));
   CIR_TRY(cir_make_map_2d(ctx, &mw, a->w, w_rows, DM, DM, SLAB_ROWS));

@@ -133,7 +133,7 @@ def qkv_probe(T=4096, L=32):
     mask = torch.ones(T, L, dtype=torch.int32).cuda()
     flops = 2 * 2 * T * L * 2304 * 768 + 4 * 2 * T * 12 * L * L * 64
     ms = timeit(lambda: e.qkv_attention(x, w, bias, key_mask=mask), warm=2, it=10)
-    print(f"fused qkv+attention T={T} L={L}: {ms:.3f} ms  {flops/ms/1e9:.0f} TF/s  (CIR_QKV_DEBUG={os.environ.get('CIR_QKV_DEBUG')})", flush=True)
+    print(f"fused qkv+attention T={T} L={L}: {ms:.3f} ms  {flops/ms/1e9:.0f} TF/s  (CIR_QKV_DRAIN={os.environ.get('CIR_QKV_DRAIN')})", flush=True)
     x2 = x.reshape(2, T * L, 768)
     ms_g = timeit(lambda: e.gemm(x2, w, bias), warm=2, it=10)
     qkv = e.gemm(x2, w, bias)[0].reshape(T, L, 2304)
