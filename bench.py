@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--gallery", type=int, default=2297)      # CIRR-val-sized token gallery (BASELINE configs[1])
     ap.add_argument("--length", type=int, default=32)
     ap.add_argument("--partition", default="candidate", choices=["candidate", "query"])
-    ap.add_argument("--cpu-sample-queries", type=int, default=2)
+    ap.add_argument("--cpu-sample-queries", type=int, default=4)      # ~13 s of CPU work on the box's 16 cores
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     a = ap.parse_args()
